@@ -1,0 +1,267 @@
+// C ABI of libgppvae_b200 (see include/gppvae_b200.h): argument validation and dispatch to the
+// kernel launchers, plus the host-buffer end-to-end entry.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gpp {
+
+static thread_local std::string g_last_error;
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cached;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+static bool mat_ok(const float* p, int64_t ld, int64_t cols) { return p && aligned16(p) && ld >= cols && ld % 4 == 0; }
+
+}  // namespace gpp
+
+using namespace gpp;
+
+extern "C" int gpp_version(void) { return 100; }
+extern "C" const char* gpp_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* gpp_gemm_engine(void) { return "simt-fp32"; }
+extern "C" uint64_t gpp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------ pass 1
+extern "C" size_t gpp_gram_workspace_bytes(int64_t n, int32_t Q, int32_t L) { return tn_workspace_bytes(n, Q, Q, L, 1); }
+
+extern "C" int gpp_gram_vtz(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int32_t Q, int32_t L,
+                            float* GC, int64_t ldgc, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(n >= 0 && Q > 0 && L >= 0 && Q % 4 == 0 && L % 4 == 0, "gram_vtz: bad shape n=%lld Q=%d L=%d",
+              (long long)n, Q, L);
+  GPP_REQUIRE(mat_ok(V, ldv, Q), "gram_vtz: V must be 16-byte aligned with ldv >= Q and ldv %% 4 == 0");
+  GPP_REQUIRE(L == 0 || mat_ok(X, ldx, L), "gram_vtz: X must be 16-byte aligned with ldx >= L and ldx %% 4 == 0");
+  GPP_REQUIRE(mat_ok(GC, ldgc, (int64_t)Q + L), "gram_vtz: GC must be 16-byte aligned with ldgc >= Q + L");
+  return launch_tn(V, ldv, Q, V, ldv, Q, X, ldx, L, n, 1, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
+}
+
+extern "C" size_t gpp_atb_workspace_bytes(int64_t n, int32_t ka, int32_t kb) { return tn_workspace_bytes(n, ka, 0, kb, 0); }
+
+extern "C" int gpp_atb(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int32_t ka, int32_t kb,
+                       float* out, int64_t ldo, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(n >= 0 && ka > 0 && kb > 0 && ka % 4 == 0 && kb % 4 == 0, "atb: bad shape");
+  GPP_REQUIRE(mat_ok(A, lda, ka) && mat_ok(B, ldb, kb) && mat_ok(out, ldo, kb), "atb: bad pointer / leading dimension");
+  return launch_tn(A, lda, ka, nullptr, 0, 0, B, ldb, kb, n, 0, nullptr, 0, out, ldo, nullptr, workspace,
+                   workspace_bytes, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ Q-space solve
+extern "C" size_t gpp_factor_state_bytes(int32_t Q) { return factor_workspace_bytes(Q); }
+extern "C" size_t gpp_solve_workspace_bytes(int32_t Q, int32_t L) { return solve_workspace_bytes(Q, L); }
+
+extern "C" int gpp_factor(const float* G, int64_t ldg, int32_t Q, const float* vs, uint32_t flags, float* Binv,
+                          double* scal, void* state, size_t state_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(Q > 0 && Q % 4 == 0, "factor: bad shape Q=%d", Q);
+  GPP_REQUIRE(mat_ok(G, ldg, Q), "factor: bad G");
+  GPP_REQUIRE(vs && scal, "factor: null vs / scal");
+  GPP_REQUIRE(!(flags & GPP_WANT_BINV) || (Binv && aligned16(Binv)), "factor: Binv required with GPP_WANT_BINV");
+  return launch_factor(G, ldg, Q, vs, flags, Binv, scal, state, state_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int gpp_solve_w(const float* C, int64_t ldc, int32_t Q, int32_t L, int32_t L_true, int64_t n_total,
+                           float* W, int64_t ldw, double* scal, const void* state, size_t state_bytes, void* workspace,
+                           size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(Q > 0 && L > 0 && Q % 4 == 0 && L % 4 == 0 && n_total > 0 && L_true > 0 && L_true <= L,
+              "solve_w: bad shape Q=%d L=%d L_true=%d", Q, L, L_true);
+  GPP_REQUIRE(mat_ok(C, ldc, L) && mat_ok(W, ldw, L) && scal, "solve_w: bad C / W / scal");
+  return launch_solve_w(C, ldc, Q, L, L_true, n_total, W, ldw, scal, state, state_bytes, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int gpp_factor_solve(const float* GC, int64_t ldgc, int32_t Q, int32_t L, const float* vs, int64_t n_total,
+                                uint32_t flags, float* W, int64_t ldw, float* Binv, double* scal, void* workspace,
+                                size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(Q > 0 && L > 0 && Q % 4 == 0 && L % 4 == 0 && n_total > 0, "factor_solve: bad shape Q=%d L=%d", Q, L);
+  GPP_REQUIRE(mat_ok(GC, ldgc, (int64_t)Q + L), "factor_solve: bad GC");
+  const size_t sb = align_up(factor_workspace_bytes(Q), 256);
+  if (!workspace || workspace_bytes < sb + solve_workspace_bytes(Q, L)) {
+    set_error("factor_solve: workspace too small (%zu < %zu bytes)", workspace_bytes, sb + solve_workspace_bytes(Q, L));
+    return GPP_ERR_WORKSPACE;
+  }
+  GPP_TRY(gpp_factor(GC, ldgc, Q, vs, flags, Binv, scal, workspace, sb, stream));
+  return gpp_solve_w(GC + Q, ldgc, Q, L, L, n_total, W, ldw, scal, workspace, sb, static_cast<char*>(workspace) + sb,
+                     workspace_bytes - sb, stream);
+}
+
+// ------------------------------------------------------------------ pass 2
+extern "C" size_t gpp_xb_workspace_bytes(int64_t n, int32_t Q, int32_t L) {
+  (void)Q;
+  return xb_workspace_bytes(n, L);
+}
+
+extern "C" int gpp_xb_nll(const float* V, int64_t ldv, const float* X, int64_t ldx, const float* W, int64_t ldw,
+                          int64_t n, int32_t Q, int32_t L, double* scal, float* Xb, int64_t ldxb, float* nll,
+                          void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(n >= 0 && Q > 0 && L > 0 && Q % 4 == 0 && L % 4 == 0, "xb_nll: bad shape");
+  GPP_REQUIRE(mat_ok(V, ldv, Q) && mat_ok(X, ldx, L) && mat_ok(W, ldw, L) && mat_ok(Xb, ldxb, L),
+              "xb_nll: bad pointer / leading dimension");
+  GPP_REQUIRE(scal && nll, "xb_nll: null scal / nll");
+  return launch_xb(V, ldv, X, ldx, W, ldw, n, Q, L, scal, 0.f, Xb, ldxb, nll, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int gpp_x_minus_am(const float* X, int64_t ldx, const float* A, int64_t lda, const float* M, int64_t ldm,
+                              int64_t n, int32_t k, int32_t m, float alpha, float* out, int64_t ldo,
+                              gpp_stream_t stream) {
+  GPP_REQUIRE(n >= 0 && k > 0 && m > 0 && k % 4 == 0 && m % 4 == 0, "x_minus_am: bad shape");
+  GPP_REQUIRE(mat_ok(X, ldx, m) && mat_ok(A, lda, k) && mat_ok(M, ldm, m) && mat_ok(out, ldo, m),
+              "x_minus_am: bad pointer / leading dimension");
+  return launch_xb(A, lda, X, ldx, M, ldm, n, k, m, nullptr, alpha, out, ldo, nullptr, nullptr, 0,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int gpp_vbs(const double* scal, int64_t n_total, int32_t Q, int32_t L, float* vbs, gpp_stream_t stream) {
+  GPP_REQUIRE(scal && vbs && n_total > 0 && Q > 0 && L > 0, "vbs: bad argument");
+  return launch_vbs(scal, n_total, Q, L, vbs, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ Vb
+extern "C" size_t gpp_vb_workspace_bytes(int64_t n, int32_t Q, int32_t L) {
+  (void)n; (void)Q; (void)L;
+  return 0;
+}
+
+extern "C" int gpp_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const float* Binv, const float* W,
+                      int64_t ldw, const double* scal, int64_t n, int32_t Q, int32_t L, int32_t L_true, float* Vb,
+                      int64_t ldvb, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  GPP_REQUIRE(n >= 0 && Q > 0 && L > 0 && Q % 4 == 0 && L % 4 == 0 && L_true > 0 && L_true <= L, "vb: bad shape");
+  GPP_REQUIRE(mat_ok(V, ldv, Q) && mat_ok(Xb, ldxb, L) && mat_ok(W, ldw, L) && mat_ok(Vb, ldvb, Q) && Binv &&
+                  aligned16(Binv) && scal,
+              "vb: bad pointer / leading dimension");
+  return launch_vb(V, ldv, Xb, ldxb, Binv, Q, W, ldw, scal, n, Q, L, L_true, Vb, ldvb, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host-buffer entry
+namespace gpp {
+__global__ void softmax2_kernel(const float* __restrict__ lvs, float* __restrict__ vs) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double v0, vn;
+    softmax2(lvs, v0, vn);
+    vs[0] = (float)v0;
+    vs[1] = (float)vn;
+  }
+}
+}  // namespace gpp
+
+struct gpp_host_ctx {
+  cudaStream_t stream = nullptr;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+};
+
+extern "C" int gpp_host_ctx_create(gpp_host_ctx** ctx) {
+  GPP_REQUIRE(ctx, "host_ctx_create: null");
+  gpp_host_ctx* c = new gpp_host_ctx();
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    return GPP_ERR_CUDA;
+  }
+  *ctx = c;
+  return GPP_OK;
+}
+
+extern "C" int gpp_host_ctx_destroy(gpp_host_ctx* ctx) {
+  if (!ctx) return GPP_OK;
+  if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GPP_OK;
+}
+
+extern "C" int gpp_gp_term_host(gpp_host_ctx* ctx, const float* x0_host, int64_t P, int32_t p, const float* v0_host,
+                                int64_t nviews, int32_t q, const int64_t* d_host, const int64_t* w_host,
+                                const float* X_host, int64_t n, int32_t L, const float* lvs_host, float* nll_host,
+                                float* Xb_host, float* vbs_host) {
+  GPP_REQUIRE(ctx && x0_host && v0_host && d_host && w_host && X_host && lvs_host && nll_host,
+              "gp_term_host: null pointer");
+  GPP_REQUIRE(P > 0 && p > 0 && nviews > 0 && q > 0 && n > 0 && L > 0, "gp_term_host: bad shape");
+  const int64_t Q64 = (int64_t)p * q;
+  GPP_REQUIRE(Q64 % 4 == 0 && L % 4 == 0 && Q64 < (1 << 30), "gp_term_host: p*q and L must be multiples of 4");
+  const int Q = (int)Q64;
+  cudaStream_t st = ctx->stream;
+
+  // carve the device arena
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  const size_t o_x0 = take((size_t)P * p * 4), o_xn = take((size_t)P * p * 4);
+  const size_t o_v0 = take((size_t)nviews * q * 4), o_wn = take((size_t)nviews * q * 4);
+  const size_t o_d = take((size_t)n * 8), o_w = take((size_t)n * 8);
+  const size_t o_lvs = take(16), o_vs = take(16), o_scal = take(GPP_NSCAL * 8), o_vbs = take(16);
+  const size_t o_X = take((size_t)n * L * 4), o_Xb = take((size_t)n * L * 4), o_nll = take((size_t)n * 4);
+  const size_t o_V = take((size_t)n * Q * 4);
+  const size_t o_GC = take((size_t)Q * (Q + L) * 4), o_W = take((size_t)Q * L * 4);
+  const size_t b_gram = gpp_gram_workspace_bytes(n, Q, L), b_fac = align_up(gpp_factor_state_bytes(Q), 256) + gpp_solve_workspace_bytes(Q, L),
+               b_xb = gpp_xb_workspace_bytes(n, Q, L);
+  size_t b_ws = b_gram > b_fac ? b_gram : b_fac;
+  if (b_xb > b_ws) b_ws = b_xb;
+  const size_t o_ws = take(b_ws);
+  if (off > ctx->arena_bytes) {
+    if (ctx->arena) GPP_CUDA(cudaFree(ctx->arena));
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    GPP_CUDA(cudaMalloc(&ctx->arena, off));
+    ctx->arena_bytes = off;
+  }
+  char* a = static_cast<char*>(ctx->arena);
+  auto F = [&](size_t o) { return reinterpret_cast<float*>(a + o); };
+  int64_t* d_dev = reinterpret_cast<int64_t*>(a + o_d);
+  int64_t* w_dev = reinterpret_cast<int64_t*>(a + o_w);
+  double* scal = reinterpret_cast<double*>(a + o_scal);
+
+  GPP_CUDA(cudaMemcpyAsync(F(o_x0), x0_host, (size_t)P * p * 4, cudaMemcpyHostToDevice, st));
+  GPP_CUDA(cudaMemcpyAsync(F(o_v0), v0_host, (size_t)nviews * q * 4, cudaMemcpyHostToDevice, st));
+  GPP_CUDA(cudaMemcpyAsync(d_dev, d_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  GPP_CUDA(cudaMemcpyAsync(w_dev, w_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  GPP_CUDA(cudaMemcpyAsync(F(o_lvs), lvs_host, 8, cudaMemcpyHostToDevice, st));
+  GPP_CUDA(cudaMemcpyAsync(F(o_X), X_host, (size_t)n * L * 4, cudaMemcpyHostToDevice, st));
+
+  GPP_TRY(gpp_normalize_rows_fwd(F(o_x0), P, p, F(o_xn), st));
+  GPP_TRY(gpp_normalize_rows_fwd(F(o_v0), nviews, q, F(o_wn), st));
+  GPP_TRY(gpp_khatri_rao_fwd(F(o_xn), P, p, F(o_wn), nviews, q, d_dev, w_dev, n, F(o_V), Q, st));
+  GPP_TRY(gpp_gram_vtz(F(o_V), Q, F(o_X), L, n, Q, L, F(o_GC), Q + L, a + o_ws, b_ws, st));
+  softmax2_kernel<<<1, 32, 0, st>>>(F(o_lvs), F(o_vs));
+  GPP_LAUNCH_CHECK();
+  GPP_TRY(gpp_factor_solve(F(o_GC), Q + L, Q, L, F(o_vs), n, 0, F(o_W), L, nullptr, scal, a + o_ws, b_ws, st));
+  GPP_TRY(gpp_xb_nll(F(o_V), Q, F(o_X), L, F(o_W), L, n, Q, L, scal, F(o_Xb), L, F(o_nll), a + o_ws, b_ws, st));
+  GPP_TRY(gpp_vbs(scal, n, Q, L, F(o_vbs), st));
+
+  GPP_CUDA(cudaMemcpyAsync(nll_host, F(o_nll), (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (Xb_host) GPP_CUDA(cudaMemcpyAsync(Xb_host, F(o_Xb), (size_t)n * L * 4, cudaMemcpyDeviceToHost, st));
+  if (vbs_host) GPP_CUDA(cudaMemcpyAsync(vbs_host, F(o_vbs), 8, cudaMemcpyDeviceToHost, st));
+  GPP_CUDA(cudaStreamSynchronize(st));
+  return GPP_OK;
+}

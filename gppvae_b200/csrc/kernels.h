@@ -1,0 +1,46 @@
+// Internal launch interface between the translation units of libgppvae_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace gpp {
+
+// ---- gemm_simt.cu ----
+struct GemmParams {
+  const float* A; int64_t lda; int64_t strideA;
+  const float* B; int64_t ldb; int64_t strideB;
+  float* C; int64_t ldc; int64_t strideC;
+  int M, N, K;
+  int M_last;      // >= 0: rows of the last batch (ragged final pair of the triangular inverse)
+  int K_is_M;      // contraction length equals this batch's M
+  float alpha, beta;
+  int lower_only;  // skip tiles strictly above the block diagonal
+  int tri_a;       // A(m, k) == 0 for k > m : stop the contraction at the tile's last row
+  int tri_b;       // B(n, k) == 0 for k < n : start the contraction at the tile's first column
+};
+int launch_gemm(const GemmParams& p, bool a_rowc, bool b_rowc, int batches, cudaStream_t st);
+
+size_t tn_workspace_bytes(int64_t n, int ka, int kb1, int kb2, int symmetric);
+int launch_tn(const float* A, int64_t lda, int ka, const float* B1, int64_t ldb1, int kb1, const float* B2,
+              int64_t ldb2, int kb2, int64_t n, int symmetric, float* out, int64_t ldo, float* out2, int64_t ldo2,
+              const double* scal_for_b2, void* ws, size_t ws_bytes, cudaStream_t st);
+
+size_t xb_workspace_bytes(int64_t n, int L);
+int launch_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n, int Q,
+              int L, double* scal, float alpha_host, float* Xb, int64_t ldxb, float* nll, void* ws, size_t ws_bytes,
+              cudaStream_t st);
+int launch_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const float* Binv, int64_t ldb,
+              const float* W, int64_t ldw, const double* scal, int64_t n, int Q, int L, int L_true, float* Vb,
+              int64_t ldvb, cudaStream_t st);
+
+// ---- qspace.cu ----
+size_t factor_workspace_bytes(int Q);
+size_t solve_workspace_bytes(int Q, int L);
+int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t flags, float* Binv, double* scal,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_solve_w(const float* C, int64_t ldc, int Q, int L, int L_true, int64_t n_total, float* W, int64_t ldw,
+                   double* scal, const void* state, size_t state_bytes, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_vbs(const double* scal, int64_t n_total, int Q, int L, float* vbs, cudaStream_t st);
+
+}  // namespace gpp

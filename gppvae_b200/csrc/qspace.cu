@@ -1,0 +1,351 @@
+// Q-space solve (replicated on every rank): from GC = V^T [V | X] and lvs
+//   B = I + (v0/vn) G = Lc Lc^T      blocked right-looking Cholesky, 64-wide panels; the diagonal
+//                                    block is factored AND inverted in shared memory / registers by
+//                                    one 64-thread CTA, which turns the panel TRSM into a GEMM
+//   log|B| = 2 sum log diag(Lc)      (replaces the svd of gp.py:33 through the determinant lemma)
+//   Linv   = Lc^-1                   recursive-doubling triangular inverse (log2(Q/64) batched levels)
+//   [Binv | W] = Linv^T [Linv | (v0/vn) Linv C]   (replaces torch.inverse of gp.py:35)
+// Q is padded to Qp (multiple of 64) with an identity block, which changes neither log|B| nor W.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gpp {
+
+constexpr int NB = 64;  // Cholesky panel width
+
+// ------------------------------------------------------------------ scalars
+__global__ void scal_init_kernel(const float* __restrict__ vs, double* __restrict__ scal) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    scal[GPP_S_V0] = (double)vs[0];
+    scal[GPP_S_VN] = (double)vs[1];
+  }
+}
+
+// Bm (Qp x Qp) = I + (v0/vn) G on the real Q x Q block, identity on the padding.
+__global__ void __launch_bounds__(256) build_b_kernel(const float* __restrict__ G, int64_t ldg, int Q, int Qp,
+                                                      const double* __restrict__ scal, float* __restrict__ Bm) {
+  const float r = (float)(scal[GPP_S_V0] / scal[GPP_S_VN]);
+  const int64_t total4 = (int64_t)Qp * (Qp / 4);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / (Qp / 4));
+    const int j4 = (int)(e - (int64_t)i * (Qp / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < Q && j4 < Q) {  // Q % 4 == 0, so a float4 never straddles the edge
+      const float4 g = *reinterpret_cast<const float4*>(G + (int64_t)i * ldg + j4);
+      v = make_float4(r * g.x, r * g.y, r * g.z, r * g.w);
+    }
+    if (i == j4 + 0) v.x += 1.f;
+    if (i == j4 + 1) v.y += 1.f;
+    if (i == j4 + 2) v.z += 1.f;
+    if (i == j4 + 3) v.w += 1.f;
+    *reinterpret_cast<float4*>(Bm + (int64_t)i * Qp + j4) = v;
+  }
+}
+
+// ------------------------------------------------------------------ diagonal block: factor + invert
+// One CTA of 64 threads; thread i owns row i of the 64 x 64 block in registers.
+// On exit A holds L (lower, zeros above) and Dinv holds L^-1 (lower, zeros above).
+__global__ void __launch_bounds__(NB) potf2_inv_kernel(float* __restrict__ A, int64_t lda, float* __restrict__ Dinv,
+                                                       int64_t ldd) {
+  __shared__ float Ls[NB][NB + 1];
+  __shared__ float Xs[NB][NB + 1];
+  __shared__ float colbuf[2][NB];
+  __shared__ float rdiag[NB];
+  const int i = threadIdx.x;
+  for (int r = 0; r < NB; ++r) Ls[r][i] = A[(int64_t)r * lda + i];
+  __syncthreads();
+  float a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) a[c] = Ls[i][c];
+
+  // right-looking Cholesky, one barrier per column (colbuf is double buffered)
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    colbuf[j & 1][i] = a[j];
+    __syncthreads();
+    const float piv = colbuf[j & 1][j];
+    const float dj = sqrtf(piv);
+    const float rinv = 1.f / dj;
+    const float lij = (i == j) ? dj : a[j] * rinv;
+    a[j] = lij;
+    if (i > j) {
+#pragma unroll
+      for (int c = j + 1; c < NB; ++c) a[c] = fmaf(-lij, colbuf[j & 1][c] * rinv, a[c]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    Ls[i][c] = (c <= i) ? a[c] : 0.f;
+    if (c == i) rdiag[i] = 1.f / a[c];  // static register index: no local-memory spill of a[]
+  }
+  __syncthreads();
+
+  // column i of X = L^-1 by forward substitution (all reads of Ls are warp-uniform broadcasts)
+  float x[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < r; ++k) {
+      const float t = Ls[r][k] * x[k];
+      if ((k & 3) == 0) s0 += t;
+      else if ((k & 3) == 1) s1 += t;
+      else if ((k & 3) == 2) s2 += t;
+      else s3 += t;
+    }
+    const float rhs = (r == i) ? 1.f : 0.f;
+    x[r] = (rhs - ((s0 + s1) + (s2 + s3))) * rdiag[r];
+  }
+#pragma unroll
+  for (int r = 0; r < NB; ++r) Xs[r][i] = (r >= i) ? x[r] : 0.f;
+  __syncthreads();
+  for (int r = 0; r < NB; ++r) {
+    A[(int64_t)r * lda + i] = Ls[r][i];
+    Dinv[(int64_t)r * ldd + i] = Xs[r][i];
+  }
+}
+
+// ------------------------------------------------------------------ reductions
+// partials[blockIdx.x] = sum over this CTA's rows of sum_{c < cols} A[r][c]^2 (fixed order)
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ A, int64_t ld, int rows, int cols,
+                                                            double* __restrict__ partials) {
+  __shared__ double red[8];
+  double s = 0;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x)
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      const double v = (double)A[(int64_t)r * ld + c];
+      s += v * v;
+    }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
+constexpr int kSumsqBlocks = 256;
+
+// deterministic single-CTA sum of `nparts` doubles (+ optional 2 sum log diag(Lc))
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0;
+  for (int w = 0; w < 8; ++w) t += red[w];
+  __syncthreads();
+  return t;
+}
+
+// after the factorisation: logdetB from diag(Lc), tr Binv from the partial sums of Linv^2
+__global__ void __launch_bounds__(256) factor_scalars_kernel(const float* __restrict__ Lc, int Qp, int Q,
+                                                             const double* __restrict__ part_linv, int nparts,
+                                                             double* __restrict__ scal) {
+  __shared__ double red[8];
+  double ld = 0, tr = 0;
+  for (int i = threadIdx.x; i < Q; i += blockDim.x) ld += 2.0 * log((double)Lc[(int64_t)i * Qp + i]);
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) tr += part_linv[i];
+  ld = block_sum_256(ld, red);
+  tr = block_sum_256(tr, red);
+  if (threadIdx.x == 0) {
+    scal[GPP_S_LOGDETB] = ld;
+    scal[GPP_S_TRBINV] = tr;
+  }
+}
+
+// after W: ||W||_F^2 and the per-row constant of the NLL
+__global__ void __launch_bounds__(256) solve_scalars_kernel(int L, int64_t n_total, const double* __restrict__ part_w,
+                                                            int nparts, double* __restrict__ scal) {
+  __shared__ double red[8];
+  double w2 = 0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) w2 += part_w[i];
+  w2 = block_sum_256(w2, red);
+  if (threadIdx.x == 0) {
+    scal[GPP_S_WNORM2] = w2;
+    scal[GPP_S_ROWCONST] = 0.5 * (double)L * (log(scal[GPP_S_VN]) + scal[GPP_S_LOGDETB] / (double)n_total);
+  }
+}
+
+// vbs (gp.py:75-76, 79-81) in Q-space form:
+//   vbs[0] = -0.5 ||W||^2 / v0^2 + 0.5 L (Q - tr Binv) / (r vn),  r = v0/vn
+//   vbs[1] = -0.5 ||Xb||^2      + 0.5 L (N - Q + tr Binv) / vn
+__global__ void vbs_kernel(const double* __restrict__ scal, int64_t n_total, int Q, int L, float* __restrict__ vbs) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double v0 = scal[GPP_S_V0], vn = scal[GPP_S_VN];
+    const double trb = scal[GPP_S_TRBINV];
+    vbs[0] = (float)(-0.5 * scal[GPP_S_WNORM2] / (v0 * v0) + 0.5 * (double)L * ((double)Q - trb) / v0);
+    vbs[1] = (float)(-0.5 * scal[GPP_S_XB2] + 0.5 * (double)L * ((double)n_total - (double)Q + trb) / vn);
+  }
+}
+
+int launch_vbs(const double* scal, int64_t n_total, int Q, int L, float* vbs, cudaStream_t st) {
+  vbs_kernel<<<1, 32, 0, st>>>(scal, n_total, Q, L, vbs);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
+// ------------------------------------------------------------------ driver
+// The factor workspace doubles as the factorisation *state*: after launch_factor() it holds Lc and
+// Linv, which launch_solve_w() reuses for any number of right-hand sides (train_gppvae.py builds the
+// same factorisation twice per epoch, at :235 and inside :166; the caller caches this buffer).
+struct FactorLayout {
+  int Qp;
+  size_t off_bm, off_linv, off_tm, off_part, off_tn, total;
+  size_t tn_bytes;
+};
+
+static FactorLayout factor_layout(int Q) {
+  FactorLayout f;
+  f.Qp = (int)(ceil_div(Q, NB) * NB);
+  const size_t qq = align_up((size_t)f.Qp * f.Qp * sizeof(float), 256);
+  size_t o = 0;
+  f.off_bm = o;   o += qq;
+  f.off_linv = o; o += qq;
+  f.off_tm = o;   o += qq;
+  f.off_part = o; o += align_up((size_t)kSumsqBlocks * sizeof(double), 256);
+  f.off_tn = o;
+  f.tn_bytes = tn_workspace_bytes(Q, Q, Q, 0, 1);
+  o += align_up(f.tn_bytes, 256);
+  f.total = o;
+  return f;
+}
+
+struct SolveLayout {
+  size_t off_t1, off_part, off_tn, total;
+  size_t tn_bytes;
+};
+
+static SolveLayout solve_layout(int Q, int L) {
+  SolveLayout f;
+  size_t o = 0;
+  f.off_t1 = o;   o += align_up((size_t)Q * L * sizeof(float), 256);
+  f.off_part = o; o += align_up((size_t)kSumsqBlocks * sizeof(double), 256);
+  f.off_tn = o;
+  f.tn_bytes = tn_workspace_bytes(Q, Q, 0, L, 0);
+  o += align_up(f.tn_bytes, 256);
+  f.total = o;
+  return f;
+}
+
+size_t factor_workspace_bytes(int Q) { return factor_layout(Q).total; }
+size_t solve_workspace_bytes(int Q, int L) { return solve_layout(Q, L).total; }
+
+int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t flags, float* Binv, double* scal,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+  const FactorLayout f = factor_layout(Q);
+  if (!ws || ws_bytes < f.total) {
+    set_error("factor: workspace too small (%zu < %zu bytes)", ws_bytes, f.total);
+    return GPP_ERR_WORKSPACE;
+  }
+  char* base = static_cast<char*>(ws);
+  float* Bm = reinterpret_cast<float*>(base + f.off_bm);
+  float* Linv = reinterpret_cast<float*>(base + f.off_linv);
+  float* Tm = reinterpret_cast<float*>(base + f.off_tm);
+  double* part = reinterpret_cast<double*>(base + f.off_part);
+  void* tnws = base + f.off_tn;
+  const int Qp = f.Qp;
+  const int nb = Qp / NB;
+
+  scal_init_kernel<<<1, 32, 0, st>>>(vs, scal);
+  GPP_LAUNCH_CHECK();
+  {
+    const int64_t total4 = (int64_t)Qp * (Qp / 4);
+    int blocks = (int)(ceil_div(total4, 256) < 4096 ? ceil_div(total4, 256) : 4096);
+    build_b_kernel<<<blocks, 256, 0, st>>>(G, ldg, Q, Qp, scal, Bm);
+    GPP_LAUNCH_CHECK();
+  }
+  GPP_CUDA(cudaMemsetAsync(Linv, 0, (size_t)Qp * Qp * sizeof(float), st));
+
+  // ---- blocked right-looking Cholesky
+  for (int j = 0; j < nb; ++j) {
+    const int k0 = j * NB;
+    float* diag = Bm + (int64_t)k0 * (Qp + 1);
+    float* dinv = Linv + (int64_t)k0 * (Qp + 1);
+    potf2_inv_kernel<<<1, NB, 0, st>>>(diag, Qp, dinv, Qp);
+    GPP_LAUNCH_CHECK();
+    const int rem = Qp - k0 - NB;
+    if (rem <= 0) break;
+    float* panel = Bm + (int64_t)(k0 + NB) * Qp + k0;  // A21, becomes L21 in place
+    GemmParams p{};
+    p.A = panel; p.lda = Qp; p.B = dinv; p.ldb = Qp; p.C = panel; p.ldc = Qp;
+    p.M = rem; p.N = NB; p.K = NB; p.M_last = -1; p.alpha = 1.f; p.beta = 0.f;
+    GPP_TRY(launch_gemm(p, false, false, 1, st));  // L21 = A21 . Dinv^T
+    GemmParams s{};
+    s.A = panel; s.lda = Qp; s.B = panel; s.ldb = Qp;
+    s.C = Bm + (int64_t)(k0 + NB) * (Qp + 1); s.ldc = Qp;
+    s.M = rem; s.N = rem; s.K = NB; s.M_last = -1; s.alpha = -1.f; s.beta = 1.f; s.lower_only = 1;
+    GPP_TRY(launch_gemm(s, false, false, 1, st));  // A22 -= L21 . L21^T (lower tiles)
+  }
+
+  // ---- Linv by recursive doubling: inv([[A,0],[C,D]]) = [[Ai,0],[-Di C Ai, Di]]
+  for (int b = NB; b < Qp; b *= 2) {
+    const int npairs = (int)ceil_div(Qp - b, 2 * b);
+    int m_last = Qp - (2 * (npairs - 1) * b + b);  // rows of the last pair's D block
+    if (m_last > b) m_last = b;                    // (a trailing unpaired block waits for the next level)
+    const int64_t pair_stride = (int64_t)2 * b * (Qp + 1);
+    GemmParams t{};
+    t.A = Bm + (int64_t)b * Qp;  t.lda = Qp; t.strideA = pair_stride;      // C block of Lc
+    t.B = Linv;                  t.ldb = Qp; t.strideB = pair_stride;      // Ai, read as B(n,k) = Ai[k][n]
+    t.C = Tm + (int64_t)b * Qp;  t.ldc = Qp; t.strideC = pair_stride;
+    t.M = b; t.N = b; t.K = b; t.M_last = m_last; t.alpha = 1.f; t.beta = 0.f; t.tri_b = 1;
+    GPP_TRY(launch_gemm(t, false, true, npairs, st));                      // T = C . Ai
+    GemmParams x{};
+    x.A = Linv + (int64_t)b * (Qp + 1); x.lda = Qp; x.strideA = pair_stride;  // Di
+    x.B = Tm + (int64_t)b * Qp;         x.ldb = Qp; x.strideB = pair_stride;  // T, read as B(n,k) = T[k][n]
+    x.C = Linv + (int64_t)b * Qp;       x.ldc = Qp; x.strideC = pair_stride;
+    x.M = b; x.N = b; x.K = b; x.K_is_M = 1; x.M_last = m_last; x.alpha = -1.f; x.beta = 0.f; x.tri_a = 1;
+    GPP_TRY(launch_gemm(x, false, true, npairs, st));                      // X = -Di . T
+  }
+
+  if (flags & GPP_WANT_BINV) {  // Binv = Linv^T Linv
+    if (!Binv) {
+      set_error("factor: GPP_WANT_BINV set but Binv is null");
+      return GPP_ERR_INVALID_ARGUMENT;
+    }
+    GPP_TRY(launch_tn(Linv, Qp, Q, Linv, Qp, Q, nullptr, 0, 0, Q, 1, Binv, Q, nullptr, 0, nullptr, tnws, f.tn_bytes, st));
+  }
+  sumsq_partial_kernel<<<kSumsqBlocks, 256, 0, st>>>(Linv, Qp, Q, Q, part);
+  GPP_LAUNCH_CHECK();
+  factor_scalars_kernel<<<1, 256, 0, st>>>(Bm, Qp, Q, part, kSumsqBlocks, scal);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
+// W = (v0/vn) Linv^T (Linv C) for C (Q x L); `state` is the workspace launch_factor filled for the same Q.
+// L_true (<= L) is the number of real latent columns (the rest is zero padding) and enters ROWCONST.
+int launch_solve_w(const float* C, int64_t ldc, int Q, int L, int L_true, int64_t n_total, float* W, int64_t ldw,
+                   double* scal, const void* state, size_t state_bytes, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const FactorLayout f = factor_layout(Q);
+  const SolveLayout sl = solve_layout(Q, L);
+  if (!state || state_bytes < f.total) {
+    set_error("solve_w: factorisation state too small (%zu < %zu bytes)", state_bytes, f.total);
+    return GPP_ERR_WORKSPACE;
+  }
+  if (!ws || ws_bytes < sl.total) {
+    set_error("solve_w: workspace too small (%zu < %zu bytes)", ws_bytes, sl.total);
+    return GPP_ERR_WORKSPACE;
+  }
+  const float* Linv = reinterpret_cast<const float*>(static_cast<const char*>(state) + f.off_linv);
+  char* base = static_cast<char*>(ws);
+  float* T1 = reinterpret_cast<float*>(base + sl.off_t1);
+  double* part = reinterpret_cast<double*>(base + sl.off_part);
+  void* tnws = base + sl.off_tn;
+  const int Qp = f.Qp;
+  GemmParams g{};
+  g.A = Linv; g.lda = Qp; g.B = C; g.ldb = ldc; g.C = T1; g.ldc = L;
+  g.M = Q; g.N = L; g.K = Q; g.M_last = -1; g.alpha = 1.f; g.beta = 0.f; g.tri_a = 1;
+  GPP_TRY(launch_gemm(g, false, true, 1, st));  // T1 = Linv . C
+  GPP_TRY(launch_tn(Linv, Qp, Q, nullptr, 0, 0, T1, L, L, Q, 0, nullptr, 0, W, ldw, scal, tnws, sl.tn_bytes, st));
+  sumsq_partial_kernel<<<kSumsqBlocks, 256, 0, st>>>(W, ldw, Q, L, part);
+  GPP_LAUNCH_CHECK();
+  solve_scalars_kernel<<<1, 256, 0, st>>>(L_true, n_total, part, kSumsqBlocks, scal);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
+}  // namespace gpp

@@ -1,0 +1,307 @@
+"""Drop-in `GP` module: the reference's gp.py API on top of the sm_100a kernels.
+
+Same class name, constructor, parameter (`lvs`), method names, argument order, shapes and detach
+semantics as /root/reference/pysrc/faceplace/gp.py:11-133, so `from gppvae_b200 import GP` can stand
+where `from gp import GP` stood in train_gppvae.py:11.  Underneath, the reference's op sequence
+(U, B = U^T U + I, svd, inverse, U B^-1, two GEMMs per solve) is replaced by the Q-space algorithm of
+SURVEY.md section 7.2:
+
+    pass 1    GC = V^T [V | X]                       gpp_gram_vtz     (+ NCCL all-reduce when sharded)
+    factor    B = I + (v0/vn) G = Lc Lc^T, Linv      gpp_factor       (cached, see `_FactorCache`)
+    solve     W = (v0/vn) B^-1 C                     gpp_solve_w
+    pass 2    Xb = (X - V W)/vn, nll, sum Xb^2       gpp_xb_nll
+    extras    vbs, Vb                                gpp_vbs, gpp_vb
+
+Row sharding: construct with `process_group=` (or call `shard_rows(group)`); X and V are then this
+rank's rows, GC and sum Xb^2 are all-reduced over the group and every rank holds identical W.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from ._lib import S_QUAD, S_XB2
+
+
+class LowRankFactor:
+    """What `GP.U_UBi_Shb` returns in place of the reference's dense `U` and `UBi` (gp.py:24-38).
+
+    The reference materialises two extra N x Q tensors only to hand them back to `GP.solve`
+    (train_gppvae.py:235-236).  This handle carries V, vs and the factorisation instead; `dense()`
+    materialises the reference tensor on request.
+    """
+
+    def __init__(self, kind: str, V: torch.Tensor, ldv: int, Q: int, Qtrue: int, vs: torch.Tensor,
+                 fac: ops.Factorisation):
+        self.kind, self.V, self.ldv, self.Q, self.Qtrue, self.vs, self.fac = kind, V, ldv, Q, Qtrue, vs, fac
+        self.n = V.shape[0]
+        self.shape = torch.Size((self.n, Qtrue))
+
+    def dense(self) -> torch.Tensor:
+        vs = self.vs.detach()
+        r = torch.sqrt(vs[0] / vs[-1])
+        if self.kind == "U":
+            return r * self.V[:, : self.Qtrue]
+        if self.fac.Binv is None:
+            raise RuntimeError("UBi.dense() needs B^-1: call GP.U_UBi_Shb(Vs, vs, want_binv=True)")
+        zeros = torch.zeros(self.n, self.Q, device=self.V.device, dtype=torch.float32)
+        VB = ops.x_minus_am(zeros, self.Q, self.V, self.ldv, self.fac.Binv, self.Q, self.n, self.Q, self.Q, -1.0)
+        return r * VB[:, : self.Qtrue]
+
+
+class LazySingularValues:
+    """`Shb` of gp.py:33 (singular values of B, descending).  The trainer discards it
+    (train_gppvae.py:235), so it is only computed if somebody asks -- off the hot path, from G."""
+
+    def __init__(self, G: torch.Tensor, Qtrue: int, vs: torch.Tensor):
+        self._G, self._Q, self._vs, self._val = G, Qtrue, vs, None
+
+    def value(self) -> torch.Tensor:
+        if self._val is None:
+            vs = self._vs.detach()
+            B = torch.eye(self._Q, device=self._G.device) + (vs[0] / vs[-1]) * self._G[: self._Q, : self._Q]
+            self._val = torch.linalg.eigvalsh(B.double()).flip(0).to(torch.float32)
+        return self._val
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        args = tuple(a.value() if isinstance(a, LazySingularValues) else a for a in args)
+        return func(*args, **(kwargs or {}))
+
+
+class _FactorCache:
+    """One-entry cache of (G, factorisation) keyed on the identity and version of V and of the variances.
+
+    train_gppvae.py factors the same (Vt, vs) twice per epoch (:235 via U_UBi_Shb, then :166 inside
+    taylor_coeff).  The entry keeps a reference to V's storage so the address cannot be recycled while
+    the entry is alive; in-place updates of V or lvs bump their version counters and miss.
+    """
+
+    def __init__(self):
+        self.key = None
+        self.keep = None
+        self.G = None
+        self.ldg = 0
+        self.fac: Optional[ops.Factorisation] = None
+
+    def lookup(self, key, want_binv: bool):
+        if self.key is not None and self.key == key and (self.fac.Binv is not None or not want_binv):
+            return self.fac
+        return None
+
+    def store(self, key, keep, G, ldg, fac):
+        self.key, self.keep, self.G, self.ldg, self.fac = key, keep, G, ldg, fac
+
+
+class GP(nn.Module):
+    def __init__(self, n_rand_effs: int = 1, vsum2one: bool = True, process_group=None):
+        super().__init__()
+        if not vsum2one:
+            # the reference's other branch is broken (gp.py:52 uses an undefined name)
+            raise NotImplementedError("vsum2one=False is not implemented (it raises NameError in the reference too)")
+        if n_rand_effs != 1:
+            # the reference trainer only ever builds GP(n_rand_effs=1) (train_gppvae.py:138)
+            raise NotImplementedError("only one random-effect design (n_rand_effs=1) is implemented")
+        self.n_rand_effs = n_rand_effs
+        self.vsum2one = vsum2one
+        self.lvs = nn.Parameter(torch.zeros([n_rand_effs + 1]))      # gp.py:21-22
+        self._group = process_group
+        self._sharded = process_group is not None
+        self._cache = _FactorCache()
+        self._ntotal_cache = {}
+        self._vs_ref = None          # weakref to the tensor last returned by get_vs()
+        self._vs_version = -1
+        self.cache_hits = 0
+        self.stage_hook = None       # optional callable(name): bench.py records CUDA events at stage boundaries
+
+    # ------------------------------------------------------------------ sharding
+    def shard_rows(self, process_group=None) -> "GP":
+        """Treat the rows handed to every method as this rank's shard of the N rows."""
+        import torch.distributed as dist
+        self._group = process_group if process_group is not None else dist.group.WORLD
+        self._sharded = True
+        return self
+
+    def _all_reduce(self, t: torch.Tensor) -> None:
+        if self._sharded:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._group)
+
+    def _n_total(self, n: int, device) -> int:
+        if not self._sharded:
+            return n
+        if n not in self._ntotal_cache:     # one host sync per distinct shard size, then cached
+            t = torch.tensor([n], device=device, dtype=torch.int64)
+            self._all_reduce(t)
+            self._ntotal_cache[n] = int(t.item())
+        return self._ntotal_cache[n]
+
+    def _stage(self, name: str) -> None:
+        if self.stage_hook is not None:
+            self.stage_hook(name)
+
+    # ------------------------------------------------------------------ reference API
+    def get_vs(self) -> torch.Tensor:
+        """softmax(lvs) = [v0, vn]  (gp.py:48-50)."""
+        vs = F.softmax(self.lvs, 0)
+        self._vs_ref, self._vs_version = weakref.ref(vs), self.lvs._version
+        return vs
+
+    def _vs_token(self, vs: torch.Tensor):
+        """Cache token for a variance vector: tensors that came out of get_vs() for the current lvs are
+        all the same value; anything else is identified by object and version (and kept alive)."""
+        mine = self._vs_ref() if self._vs_ref is not None else None
+        if mine is not None and vs is mine and self._vs_version == self.lvs._version:
+            return ("lvs", id(self.lvs), self.lvs._version), None
+        return ("tensor", id(vs), vs._version), vs
+
+    def _cat(self, Vs: Sequence[torch.Tensor], vs: torch.Tensor) -> Tuple[torch.Tensor, int, int, int]:
+        """gp.py:27 for the single design the trainer uses: V passes through untouched (the sqrt(vs[0])
+        weight folds into the v0/vn factor inside the kernels).  Returns (V, ldv, Q padded, Q)."""
+        if len(Vs) != 1:
+            raise NotImplementedError(f"expected one design matrix in Vs, got {len(Vs)}")
+        Vm, ldv = ops.as_matrix(Vs[0], "V")
+        return Vm, ldv, Vm.shape[1], Vs[0].shape[1]
+
+    def _factorise(self, Vm, ldv, Q, vs, want_binv: bool, Xm=None, ldx=0, Lk=0, vs_origin=None):
+        """Pass 1 (+ all-reduce) and the factorisation, through the cache.
+        Returns (fac, C) with C = V^T X (Q x Lk, summed over ranks) or None when no X was given."""
+        n = Vm.shape[0]
+        tok, keep_vs = self._vs_token(vs if vs_origin is None else vs_origin)
+        key = (Vm.untyped_storage().data_ptr(), Vm.storage_offset(), Vm._version, n, Q, ldv, tok)
+        fac = self._cache.lookup(key, want_binv)
+        if fac is not None:
+            self.cache_hits += 1
+            C = None
+            if Lk:
+                C = ops.atb(Vm, ldv, Xm, ldx, n, Q, Lk)
+                self._all_reduce(C)
+            return fac, C
+        self._stage("pass1:start")
+        GC = ops.gram_vtz(Vm, ldv, Xm, ldx, n, Q, Lk)
+        self._stage("pass1:end")
+        self._all_reduce(GC)
+        self._stage("allreduce:end")
+        fac = ops.factor(GC, Q + Lk, Q, vs, want_binv)
+        self._stage("factor:end")
+        self._cache.store(key, (Vm, keep_vs), GC, Q + Lk, fac)
+        return fac, (GC[:, Q:] if Lk else None)
+
+    def U_UBi_Shb(self, Vs: Sequence[torch.Tensor], vs: torch.Tensor, want_binv: bool = False):
+        """gp.py:24-38.  Returns handles (see LowRankFactor) that `solve` accepts."""
+        Vm, ldv, Q, Qtrue = self._cat(Vs, vs)
+        fac, _ = self._factorise(Vm, ldv, Q, vs, want_binv)
+        U = LowRankFactor("U", Vm, ldv, Q, Qtrue, vs, fac)
+        UBi = LowRankFactor("UBi", Vm, ldv, Q, Qtrue, vs, fac)
+        return U, UBi, LazySingularValues(self._cache.G, Qtrue, vs)
+
+    def solve(self, X: torch.Tensor, U, UBi, vs: torch.Tensor) -> torch.Tensor:
+        """K^-1 X  (gp.py:40-46)."""
+        Xm, ldx = ops.as_matrix(X, "X")
+        n, L = X.shape
+        Lk = Xm.shape[1]
+        if isinstance(U, LowRankFactor):
+            if n != U.n:
+                raise ValueError(f"X has {n} rows but the factorisation was built for {U.n}")
+            C = ops.atb(U.V, U.ldv, Xm, ldx, n, U.Q, Lk)
+            self._all_reduce(C)
+            W, scal = ops.solve_w(U.fac, C, Lk, Lk, L, self._n_total(n, X.device))
+            Xb, _ = ops.xb_nll(U.V, U.ldv, Xm, ldx, W, n, U.Q, Lk, scal)
+        else:
+            # dense tensors, exactly gp.py:42-44: (X - UBi (U^T X)) / vn
+            Um, ldu = ops.as_matrix(U, "U")
+            UBm, ldub = ops.as_matrix(UBi, "UBi")
+            UX = ops.atb(Um, ldu, Xm, ldx, n, Um.shape[1], Lk)
+            self._all_reduce(UX)
+            Xb = ops.x_minus_am(Xm, ldx, UBm, ldub, UX, Lk, n, Um.shape[1], Lk, 1.0 / float(vs.detach()[-1]))
+        return Xb[:, :L] if Lk != L else Xb
+
+    def _coefficients(self, X: torch.Tensor, Vs: Sequence[torch.Tensor], want_vb: bool):
+        """Shared body of taylor_coeff and nll: returns a dict of everything computed."""
+        vs_attached = self.get_vs()
+        vs = vs_attached.detach()
+        Vm, ldv, Q, Qtrue = self._cat(Vs, vs)
+        Xm, ldx = ops.as_matrix(X, "X")
+        n, L = X.shape
+        if Vm.shape[0] != n:
+            raise ValueError(f"X has {n} rows but V has {Vm.shape[0]}")
+        if Vm.device != Xm.device:
+            raise ValueError("X and V must be on the same device")
+        Lk = Xm.shape[1]
+        n_total = self._n_total(n, X.device)
+        fac, C = self._factorise(Vm, ldv, Q, vs, want_vb, Xm, ldx, Lk, vs_origin=vs_attached)
+        W, scal = ops.solve_w(fac, C, C.stride(0), Lk, L, n_total)
+        self._stage("solve:end")
+        Xb, nll = ops.xb_nll(Vm, ldv, Xm, ldx, W, n, Q, Lk, scal)
+        self._stage("pass2:end")
+        return dict(vs=vs, Vm=Vm, ldv=ldv, Q=Q, Qtrue=Qtrue, n=n, L=L, Lk=Lk, n_total=n_total, fac=fac, W=W,
+                    scal=scal, Xb=Xb, nll=nll)
+
+    def taylor_coeff(self, X: torch.Tensor, Vs: Sequence[torch.Tensor], need_vb: bool = True
+                     ) -> Tuple[torch.Tensor, List[torch.Tensor], torch.Tensor, torch.Tensor]:
+        """gp.py:55-95: Xb = dNLL/dX, [Vb = dNLL/dV], vbs = dNLL/d[v0, vn], nll (n x 1); all detached.
+
+        `need_vb=False` (an extension) skips B^-1 and the N x Q matrix Vb and returns `[None]` in its place:
+        that is the "NLL + dNLL/dZ" evaluation BASELINE.json's metric counts."""
+        c = self._coefficients(X, Vs, need_vb)
+        scal, Q, L, Lk = c["scal"], c["Q"], c["L"], c["Lk"]
+        if self._sharded:
+            self._all_reduce(scal[S_XB2:S_QUAD + 1])
+        vbs = ops.vbs_from_scal(scal, c["n_total"], Q, L)
+        if need_vb:
+            Vb = ops.vb(c["Vm"], c["ldv"], c["Xb"], c["fac"].Binv, c["W"], scal, c["n"], Q, Lk, L)
+            Vbs = [Vb[:, : c["Qtrue"]] if c["Qtrue"] != Q else Vb]
+            self._stage("vb:end")
+        else:
+            Vbs = [None]
+        self.last_scalars = scal
+        Xb = c["Xb"][:, :L] if Lk != L else c["Xb"]
+        return Xb, Vbs, vbs, c["nll"]
+
+    def nll(self, X: torch.Tensor, Vs: Sequence[torch.Tensor]) -> torch.Tensor:
+        """gp.py:97-110.  Differentiable: backward applies the Taylor coefficients (the exact gradients
+        of sum(nll), gp.py:185-221), i.e. it is exact for a uniform upstream gradient (`.sum()`,
+        `.mean()`) -- the only way the reference ever differentiates it."""
+        return _NllFunction.apply(self, X, self.lvs, *Vs)
+
+    def nll_ineff(self, X: torch.Tensor, Vs: Sequence[torch.Tensor]) -> torch.Tensor:
+        """gp.py:112-125: O(N^3) cross-check through the dense N x N covariance.  Test utility, stock torch."""
+        vs = self.get_vs()
+        V = torch.cat([torch.sqrt(vs[i]) * Vi for i, Vi in enumerate(Vs)], 1)
+        K = V.mm(V.t()) + vs[-1] * torch.eye(X.shape[0], device=X.device, dtype=X.dtype)
+        quad = (X * torch.linalg.solve(K, X)).sum(1, keepdim=True)
+        return 0.5 * quad + 0.5 * X.shape[1] * torch.linalg.slogdet(K)[1] / X.shape[0]
+
+    def taylor_expansion(self, X: torch.Tensor, Vs: Sequence[torch.Tensor], Xb: torch.Tensor,
+                         Vbs: Sequence[torch.Tensor], vbs: torch.Tensor) -> torch.Tensor:
+        """gp.py:127-133: (n x 1) surrogate with gradients to X, each V and lvs."""
+        if len(Vs) != 1 or len(Vbs) != 1:
+            raise NotImplementedError(f"expected one design matrix in Vs / Vbs, got {len(Vs)} / {len(Vbs)}")
+        return ops._TaylorExpansion.apply(X, Vs[0], self.lvs, Xb, Vbs[0], vbs)
+
+
+class _NllFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gp: GP, X, lvs, *Vs):
+        want_grad = any(ctx.needs_input_grad[1:])
+        with torch.no_grad():
+            if want_grad:
+                Xb, Vbs, vbs, nll = gp.taylor_coeff(X, list(Vs))
+                ctx.save_for_backward(Xb, vbs, gp.get_vs().detach(), *Vbs)
+            else:
+                nll = gp._coefficients(X, list(Vs), False)["nll"]
+        return nll
+
+    @staticmethod
+    def backward(ctx, g):
+        Xb, vbs, vs, *Vbs = ctx.saved_tensors
+        gbar = g.mean()   # exact for a uniform upstream gradient (see GP.nll)
+        gX = gbar * Xb if ctx.needs_input_grad[1] else None
+        glvs = gbar * vs * (vbs - (vbs * vs).sum()) if ctx.needs_input_grad[2] else None
+        gVs = tuple(gbar * Vb if need else None for Vb, need in zip(Vbs, ctx.needs_input_grad[3:]))
+        return (None, gX, glvs, *gVs)

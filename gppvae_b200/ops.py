@@ -1,0 +1,275 @@
+"""Tensor-level wrappers over the C ABI: argument checks, layout normalisation, workspaces.
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every numerical
+operation of the hot path is a call into libgppvae_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GPP_WANT_BINV, NSCAL, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda_f32(t: torch.Tensor, name: str, ndim: int = 2) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name} must be a torch.Tensor")
+    if t.device.type != "cuda":
+        raise ValueError(f"{name} must live on a CUDA device (got {t.device}); gppvae_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32 (got {t.dtype})")
+    if t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dimensions (got shape {tuple(t.shape)})")
+
+
+def round4(c: int) -> int:
+    return (c + 3) // 4 * 4
+
+
+def as_matrix(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """Return (tensor, ld) usable by the kernels: unit column stride, 16-byte aligned rows, columns padded
+    with zeros to a multiple of 4.  Tensors that already qualify are passed through without a copy."""
+    require_cuda_f32(t, name)
+    t = t.detach()
+    n, c = t.shape
+    if c % 4 == 0 and t.data_ptr() % 16 == 0:
+        if t.is_contiguous():
+            return t, c
+        if t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.stride(0) >= c:
+            return t, t.stride(0)
+    buf = torch.zeros(n, round4(c), device=t.device, dtype=torch.float32)
+    buf[:, :c] = t
+    return buf, buf.shape[1]
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------- Vmodel
+def normalize_rows_fwd(x: torch.Tensor) -> torch.Tensor:
+    require_cuda_f32(x, "x")
+    x = x.detach().contiguous()
+    y = torch.empty_like(x)
+    check(_lib.load().gpp_normalize_rows_fwd(_p(x), x.shape[0], x.shape[1], _p(y), _stream()), "normalize_rows_fwd")
+    return y
+
+
+def normalize_rows_bwd(x: torch.Tensor, gy: torch.Tensor) -> torch.Tensor:
+    x = x.detach().contiguous()
+    gy = gy.detach().contiguous()
+    gx = torch.empty_like(x)
+    check(_lib.load().gpp_normalize_rows_bwd(_p(x), _p(gy), x.shape[0], x.shape[1], _p(gx), _stream()),
+          "normalize_rows_bwd")
+    return gx
+
+
+def _check_index(t: torch.Tensor, name: str, device) -> torch.Tensor:
+    if t.dtype != torch.int64 or t.dim() != 1:
+        raise ValueError(f"{name} must be a 1-D int64 tensor (got {t.dtype}, shape {tuple(t.shape)})")
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device} but the tables are on {device}")
+    return t.contiguous()
+
+
+def khatri_rao_fwd(xn: torch.Tensor, wn: torch.Tensor, d: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """V (n x p*q) from row-normalised tables; returns a view with the reference's shape (columns are
+    padded internally to a multiple of 4 when p*q is not one, by zero-padding p)."""
+    require_cuda_f32(xn, "xn")
+    require_cuda_f32(wn, "wn")
+    d = _check_index(d, "d", xn.device)
+    w = _check_index(w, "w", xn.device)
+    if d.shape != w.shape:
+        raise ValueError("d and w must have the same length")
+    P, p = xn.shape
+    nv, q = wn.shape
+    Q = p * q
+    xn_k, p_k = xn.detach().contiguous(), p
+    if Q % 4:
+        p_k = round4(p)
+        xn_k = torch.zeros(P, p_k, device=xn.device, dtype=torch.float32)
+        xn_k[:, :p] = xn.detach()
+    n = d.shape[0]
+    V = torch.empty(n, p_k * q, device=xn.device, dtype=torch.float32)
+    check(_lib.load().gpp_khatri_rao_fwd(_p(xn_k), P, p_k, _p(wn.detach().contiguous()), nv, q, _p(d), _p(w), n,
+                                         _p(V), V.stride(0) if n > 0 else p_k * q, _stream()), "khatri_rao_fwd")
+    return V[:, :Q] if p_k != p else V
+
+
+def khatri_rao_bwd(gV: torch.Tensor, xn: torch.Tensor, wn: torch.Tensor, d: torch.Tensor, w: torch.Tensor
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+    gV = gV.detach()
+    if gV.stride(1) != 1:
+        gV = gV.contiguous()
+    P, p = xn.shape
+    nv, q = wn.shape
+    gxn = torch.zeros_like(xn)
+    gwn = torch.zeros_like(wn)
+    check(_lib.load().gpp_khatri_rao_bwd(_p(gV), gV.stride(0), _p(xn.detach().contiguous()), P, p,
+                                         _p(wn.detach().contiguous()), nv, q, _p(d.contiguous()), _p(w.contiguous()),
+                                         d.shape[0], _p(gxn), _p(gwn), _stream()), "khatri_rao_bwd")
+    return gxn, gwn
+
+
+# ----------------------------------------------------------------------------- GP term
+def gram_vtz(V: torch.Tensor, ldv: int, X: Optional[torch.Tensor], ldx: int, n: int, Q: int, L: int) -> torch.Tensor:
+    """GC = V^T [V | X]  ->  (Q x (Q+L)) float32."""
+    lib = _lib.load()
+    GC = torch.empty(Q, Q + L, device=V.device, dtype=torch.float32)
+    ws = _workspace(lib.gpp_gram_workspace_bytes(n, Q, L), V.device)
+    check(lib.gpp_gram_vtz(_p(V), ldv, _p(X), ldx, n, Q, L, _p(GC), Q + L, _p(ws), ws.numel(), _stream()), "gram_vtz")
+    return GC
+
+
+def atb(A: torch.Tensor, lda: int, B: torch.Tensor, ldb: int, n: int, ka: int, kb: int) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(ka, kb, device=A.device, dtype=torch.float32)
+    ws = _workspace(lib.gpp_atb_workspace_bytes(n, ka, kb), A.device)
+    check(lib.gpp_atb(_p(A), lda, _p(B), ldb, n, ka, kb, _p(out), kb, _p(ws), ws.numel(), _stream()), "atb")
+    return out
+
+
+class Factorisation:
+    """State left by gpp_factor: Lc and Linv inside `state`, the scalar block, optionally Binv."""
+
+    def __init__(self, Q: int, state: torch.Tensor, scal: torch.Tensor, Binv: Optional[torch.Tensor]):
+        self.Q, self.state, self.scal, self.Binv = Q, state, scal, Binv
+
+
+def factor(G: torch.Tensor, ldg: int, Q: int, vs: torch.Tensor, want_binv: bool) -> Factorisation:
+    lib = _lib.load()
+    dev = G.device
+    state = _workspace(lib.gpp_factor_state_bytes(Q), dev)
+    scal = torch.zeros(NSCAL, device=dev, dtype=torch.float64)
+    Binv = torch.empty(Q, Q, device=dev, dtype=torch.float32) if want_binv else None
+    vs32 = vs.detach().to(torch.float32).contiguous()
+    check(lib.gpp_factor(_p(G), ldg, Q, _p(vs32), GPP_WANT_BINV if want_binv else 0, _p(Binv), _p(scal), _p(state),
+                         state.numel(), _stream()), "factor")
+    return Factorisation(Q, state, scal, Binv)
+
+
+def solve_w(f: Factorisation, C: torch.Tensor, ldc: int, L: int, L_true: int, n_total: int
+            ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """W = (v0/vn) B^-1 C and a private copy of the scalar block extended with WNORM2 / ROWCONST."""
+    lib = _lib.load()
+    W = torch.empty(f.Q, L, device=C.device, dtype=torch.float32)
+    scal = f.scal.clone()
+    ws = _workspace(lib.gpp_solve_workspace_bytes(f.Q, L), C.device)
+    check(lib.gpp_solve_w(_p(C), ldc, f.Q, L, L_true, n_total, _p(W), L, _p(scal), _p(f.state), f.state.numel(),
+                          _p(ws), ws.numel(), _stream()), "solve_w")
+    return W, scal
+
+
+def xb_nll(V, ldv, X, ldx, W, n, Q, L, scal) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    Xb = torch.empty(n, L, device=V.device, dtype=torch.float32)
+    nll = torch.empty(n, 1, device=V.device, dtype=torch.float32)
+    ws = _workspace(lib.gpp_xb_workspace_bytes(n, Q, L), V.device)
+    check(lib.gpp_xb_nll(_p(V), ldv, _p(X), ldx, _p(W), W.stride(0), n, Q, L, _p(scal), _p(Xb), L, _p(nll), _p(ws),
+                         ws.numel(), _stream()), "xb_nll")
+    return Xb, nll
+
+
+def vbs_from_scal(scal: torch.Tensor, n_total: int, Q: int, L: int) -> torch.Tensor:
+    out = torch.empty(2, device=scal.device, dtype=torch.float32)
+    check(_lib.load().gpp_vbs(_p(scal), n_total, Q, L, _p(out), _stream()), "vbs")
+    return out
+
+
+def vb(V, ldv, Xb, Binv, W, scal, n, Q, L, L_true) -> torch.Tensor:
+    Vb = torch.empty(n, Q, device=V.device, dtype=torch.float32)
+    check(_lib.load().gpp_vb(_p(V), ldv, _p(Xb), Xb.stride(0), _p(Binv), _p(W), W.stride(0), _p(scal), n, Q, L,
+                             L_true, _p(Vb), Q, None, 0, _stream()), "vb")
+    return Vb
+
+
+def x_minus_am(X, ldx, A, lda, M, ldm, n, k, m, alpha: float) -> torch.Tensor:
+    out = torch.empty(n, m, device=X.device, dtype=torch.float32)
+    check(_lib.load().gpp_x_minus_am(_p(X), ldx, _p(A), lda, _p(M), ldm, n, k, m, float(alpha), _p(out), m, _stream()),
+          "x_minus_am")
+    return out
+
+
+# ----------------------------------------------------------------------------- autograd glue
+class _NormalizeRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return normalize_rows_fwd(x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return normalize_rows_bwd(x, gy)
+
+
+class _KhatriRao(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xn, wn, d, w):
+        ctx.save_for_backward(xn, wn, d, w)
+        return khatri_rao_fwd(xn, wn, d, w)
+
+    @staticmethod
+    def backward(ctx, gV):
+        xn, wn, d, w = ctx.saved_tensors
+        gxn, gwn = khatri_rao_bwd(gV, xn, wn, d, w)
+        return gxn, gwn, None, None
+
+
+class _TaylorExpansion(torch.autograd.Function):
+    """gp.py:127-133 as one fused forward and one fused backward launch."""
+
+    @staticmethod
+    def forward(ctx, X, V, lvs, Xb, Vb, vbs):
+        lib = _lib.load()
+        Xm, ldx = as_matrix(X, "X")
+        Xbm, ldxb = as_matrix(Xb, "Xb")
+        n, L = X.shape
+        Lk = Xm.shape[1]
+        if V is not None:
+            Vm, ldv = as_matrix(V, "V")
+            Vbm, ldvb = as_matrix(Vb, "Vb")
+            Qk = Vm.shape[1]
+        else:
+            Vm = Vbm = None
+            ldv = ldvb = 4
+            Qk = 0
+        vbs32 = vbs.detach().to(torch.float32).contiguous()
+        lvs32 = lvs.detach().to(torch.float32).contiguous()
+        out = torch.empty(n, 1, device=X.device, dtype=torch.float32)
+        check(lib.gpp_taylor_expansion_fwd(_p(Xm), ldx, _p(Xbm), ldxb, _p(Vm), ldv, _p(Vbm), ldvb, n, Lk, Qk,
+                                           _p(vbs32), _p(lvs32), _p(out), _stream()), "taylor_expansion_fwd")
+        ctx.save_for_backward(Xbm, Vbm, vbs32, lvs32)
+        ctx.dims = (n, L, Lk, ldxb, (V.shape[1] if V is not None else 0), Qk, ldvb)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _lib.load()
+        Xbm, Vbm, vbs32, lvs32 = ctx.saved_tensors
+        n, L, Lk, ldxb, Q, Qk, ldvb = ctx.dims
+        g = gout.detach().to(torch.float32).contiguous().view(-1)
+        need_x, need_v, need_l = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and Vbm is not None, \
+            ctx.needs_input_grad[2]
+        gX = torch.empty(n, Lk, device=g.device, dtype=torch.float32) if need_x else None
+        gV = torch.empty(n, Qk, device=g.device, dtype=torch.float32) if need_v else None
+        gl = torch.empty(2, device=g.device, dtype=torch.float32) if need_l else None
+        check(lib.gpp_taylor_expansion_bwd(_p(g), _p(Xbm), ldxb, _p(Vbm), ldvb, n, Lk, Qk, _p(vbs32), _p(lvs32),
+                                           _p(gX), Lk, _p(gV), max(Qk, 4), _p(gl), _stream()), "taylor_expansion_bwd")
+        return (gX[:, :L] if need_x and Lk != L else gX, gV[:, :Q] if need_v and Qk != Q else gV, gl, None, None, None)
+
+
+def normalize_rows(x: torch.Tensor) -> torch.Tensor:
+    """vmod.py:10-12 with autograd (forward and backward are CUDA kernels of this library)."""
+    require_cuda_f32(x, "x")
+    return _NormalizeRows.apply(x)

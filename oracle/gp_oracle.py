@@ -101,6 +101,16 @@ def nll(X: Tensor, Vs: Sequence[Tensor], lvs: Tensor) -> Tensor:
     return _row_nll(X, woodbury_solve(X, U, UBi, vs), Shb, vs)
 
 
+def nll_and_grad(X: Tensor, Vs: Sequence[Tensor], lvs: Tensor) -> Tuple[Tensor, Tensor]:
+    """The "NLL + dNLL/dZ" evaluation BASELINE.json's metric counts: exactly the work of the reference's
+    GP.nll under no_grad (gp.py:97-110) with its local Xb = K^-1 X (gp.py:102) handed back as well."""
+    with torch.no_grad():
+        vs = variances(lvs)
+        U, UBi, Shb = woodbury_factor(Vs, vs)
+        Xb = woodbury_solve(X, U, UBi, vs)
+        return _row_nll(X, Xb, Shb, vs), Xb
+
+
 def nll_dense(X: Tensor, Vs: Sequence[Tensor], lvs: Tensor) -> Tensor:
     """O(n^3) NLL through the dense n x n covariance (reference gp.py:112-125)."""
     vs = variances(lvs)

@@ -1,0 +1,354 @@
+"""GPU parity: the CUDA path (through the C ABI / the drop-in GP and Vmodel classes) against
+
+  * the golden vectors produced by the unmodified reference (tests/golden/*.npz, fp32 and fp64), and
+  * the CPU oracle (oracle/gp_oracle.py) on seeded inputs.
+
+Tolerances are BASELINE.json's: relative error of sum(nll) <= 1e-5, max-relative error of the gradient
+dNLL/dZ (= Xb) <= 1e-4, both against the reference's own fp32 outputs; Vb and vbs[0] are graded against
+the fp64 run of the reference because the fp32 reference cancels catastrophically there.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+NLL_TOL = 1e-5      # relative error of sum(nll)            (BASELINE.json north_star)
+GRAD_TOL = 1e-4     # max-relative error of dNLL/dZ          (BASELINE.json north_star)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _cuda(a, dev, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a), dtype=dtype).to(dev)
+
+
+def _golden_V(g, dev):
+    import gppvae_b200
+    if "Vdirect" in g:
+        return _cuda(g["Vdirect"], dev), None
+    P, p = g["x0"].shape
+    nv, q = g["v0"].shape
+    vm = gppvae_b200.Vmodel(P, nv, p, q).to(dev)
+    with torch.no_grad():
+        vm.x0.copy_(_cuda(g["x0"], dev))
+        vm.v0.copy_(_cuda(g["v0"], dev))
+    return None, vm
+
+
+def test_library_is_the_cuda_one():
+    from gppvae_b200 import _lib
+    assert _lib.load().gpp_version() >= 100
+    assert _lib.gemm_engine() in ("simt-fp32", "tcgen05-3xtf32")
+
+
+def test_vmodel_forward_backward(golden, dev):
+    """vmod.py:10-12, 28-35 forward and autograd against the reference's outputs."""
+    if "Vdirect" in golden:
+        pytest.skip("case has no Vmodel")
+    _, vm = _golden_V(golden, dev)
+    d, w = _cuda(golden["d"], dev, torch.int64), _cuda(golden["w"], dev, torch.int64)
+    assert rel_err(vm.x().cpu(), golden["f32_xn"]) < 1e-6
+    assert rel_err(vm.v().cpu(), golden["f32_wn"]) < 1e-6
+    V = vm(d, w)
+    assert V.shape == golden["f32_V"].shape and V.dtype == torch.float32
+    assert rel_err(V.cpu(), golden["f32_V"]) < 1e-6
+    assert rel_err(V.cpu(), golden["f64_V"]) < 1e-6
+    probe = _cuda(np.cos(np.arange(V.numel(), dtype=np.float64)).reshape(V.shape), dev)
+    (V * probe).sum().backward()
+    assert rel_err(vm.x0.grad.cpu(), golden["f64_gx0"]) < 1e-4
+    assert rel_err(vm.v0.grad.cpu(), golden["f64_gv0"]) < 1e-4
+
+
+def _run_taylor_coeff(golden, dev):
+    import gppvae_b200
+    Vd, vm = _golden_V(golden, dev)
+    if Vd is None:
+        with torch.no_grad():
+            Vd = vm(_cuda(golden["d"], dev, torch.int64), _cuda(golden["w"], dev, torch.int64))
+    gp = gppvae_b200.GP(n_rand_effs=1).to(dev)
+    with torch.no_grad():
+        gp.lvs.copy_(_cuda(golden["lvs"], dev))
+    Z = _cuda(golden["Z"], dev)
+    return gp, Vd, Z, gp.taylor_coeff(Z, [Vd])
+
+
+def test_taylor_coeff_against_reference(golden, dev):
+    """gp.py:55-95.  NLL and dNLL/dZ within the north-star tolerances of the fp32 reference; every output
+    also graded against the fp64 reference."""
+    gp, V, Z, (Xb, Vbs, vbs, nll) = _run_taylor_coeff(golden, dev)
+    n, L = Z.shape
+    assert Xb.shape == (n, L) and nll.shape == (n, 1) and Vbs[0].shape == V.shape and vbs.shape == (2,)
+    assert not any(t.requires_grad for t in (Xb, Vbs[0], vbs, nll))
+    for tag in ("f32", "f64"):
+        ref = golden[f"{tag}_nll"].astype(np.float64).sum()
+        assert abs(nll.double().sum().item() - ref) / abs(ref) < NLL_TOL, tag
+        assert rel_err(nll.cpu(), golden[f"{tag}_nll"]) < 10 * NLL_TOL, tag
+        assert rel_err(Xb.cpu(), golden[f"{tag}_Xb"]) < GRAD_TOL, tag
+    # fp64 reference is the yard-stick for the cancellation-prone outputs; we must not be worse than
+    # a few times the fp32 reference's own error, and never worse than 2e-3.
+    ref32_vb = rel_err(golden["f32_Vb"], golden["f64_Vb"])
+    assert rel_err(Vbs[0].cpu(), golden["f64_Vb"]) < max(5 * ref32_vb, 2e-3)
+    ref32_vbs = rel_err(golden["f32_vbs"], golden["f64_vbs"])
+    assert rel_err(vbs.cpu(), golden["f64_vbs"]) < max(5 * ref32_vbs, 1e-4)
+
+
+def test_three_way_nll(golden, dev):
+    """The reference's own check 1 (gp.py:175-183): taylor_coeff / nll / nll_ineff agree."""
+    gp, V, Z, (_, _, _, nll) = _run_taylor_coeff(golden, dev)
+    with torch.no_grad():
+        a = gp.nll(Z, [V])
+        b = gp.nll_ineff(Z.double(), [V.double()])
+    assert rel_err(a.cpu(), nll.cpu()) < 1e-6
+    assert rel_err(nll.cpu(), b.cpu()) < 2e-5
+    assert rel_err(b.cpu(), golden["f64_nll_ineff"]) < 1e-5
+
+
+def test_taylor_expansion_and_gradients(golden, dev):
+    """gp.py:127-133 and the reference's own check 2 (gp.py:185-221)."""
+    gp, V, Z, (Xb, Vbs, vbs, _) = _run_taylor_coeff(golden, dev)
+    idx = _cuda(golden["mb"], dev, torch.int64)
+    # (a) surrogate on a minibatch with the REFERENCE's coefficients: isolates the fused fwd/bwd kernels
+    gXb, gVb, gvbs = _cuda(golden["f32_Xb"], dev), _cuda(golden["f32_Vb"], dev), _cuda(golden["f32_vbs"], dev)
+    xm = Z[idx].clone().requires_grad_(True)
+    vm = V[idx].clone().requires_grad_(True)
+    gp.lvs.grad = None
+    te = gp.taylor_expansion(xm, [vm], gXb[idx], [gVb[idx]], gvbs)
+    assert te.shape == (idx.numel(), 1)
+    te.sum().backward()
+    assert rel_err(te.cpu(), golden["f32_te"]) < 1e-5
+    assert rel_err(xm.grad.cpu(), golden["f32_te_gX"]) < 1e-6
+    assert rel_err(vm.grad.cpu(), golden["f32_te_gV"]) < 1e-6
+    assert rel_err(gp.lvs.grad.cpu(), golden["f32_te_glvs"]) < 1e-4
+    # (b) full batch with OUR coefficients: gradients equal the exact gradients of sum(nll) (fp64 reference)
+    xf = Z.clone().requires_grad_(True)
+    vf = V.clone().requires_grad_(True)
+    gp.lvs.grad = None
+    gp.taylor_expansion(xf, [vf], Xb, Vbs, vbs).sum().backward()
+    assert rel_err(xf.grad.cpu(), golden["f64_nll_gX"]) < GRAD_TOL
+    ref32 = rel_err(golden["f32_nll_gV"], golden["f64_nll_gV"])
+    assert rel_err(vf.grad.cpu(), golden["f64_nll_gV"]) < max(5 * ref32, 2e-3)
+    ref32 = rel_err(golden["f32_nll_glvs"], golden["f64_nll_glvs"])
+    assert rel_err(gp.lvs.grad.cpu(), golden["f64_nll_glvs"]) < max(5 * ref32, 1e-3)
+
+
+def test_nll_autograd(golden, dev):
+    """gp.nll(...).sum().backward() gives the exact gradients (gp.py:205-214)."""
+    gp, V, Z, _ = _run_taylor_coeff(golden, dev)
+    xf = Z.clone().requires_grad_(True)
+    gp.lvs.grad = None
+    gp.nll(xf, [V]).sum().backward()
+    assert rel_err(xf.grad.cpu(), golden["f64_nll_gX"]) < GRAD_TOL
+    ref32 = rel_err(golden["f32_nll_glvs"], golden["f64_nll_glvs"])
+    assert rel_err(gp.lvs.grad.cpu(), golden["f64_nll_glvs"]) < max(5 * ref32, 1e-3)
+
+
+def test_solve_handles_and_dense(golden, dev):
+    """train_gppvae.py:235-237: U_UBi_Shb + solve, with the lazy handles and with dense U / UBi tensors."""
+    gp, V, Z, _ = _run_taylor_coeff(golden, dev)
+    with torch.no_grad():
+        vs = gp.get_vs()
+        hits = gp.cache_hits
+        U, UBi, Shb = gp.U_UBi_Shb([V], vs, want_binv=True)
+        assert gp.cache_hits == hits + 1          # same (V, lvs) as the taylor_coeff above: factorisation reused
+        KiX = gp.solve(Z, U, UBi, vs)
+        assert rel_err(KiX.cpu(), golden["f32_KiX"]) < GRAD_TOL
+        assert rel_err(KiX.cpu(), golden["f64_KiX"]) < GRAD_TOL
+        assert rel_err(U.dense().cpu(), golden["f32_U"]) < 1e-6
+        assert rel_err(UBi.dense().cpu(), golden["f64_UBi"]) < 1e-4
+        assert rel_err(torch.as_tensor(Shb.value()).cpu(), golden["f64_Shb"]) < 1e-5
+        KiX2 = gp.solve(Z, _cuda(golden["f32_U"], dev), _cuda(golden["f32_UBi"], dev), vs)
+        assert rel_err(KiX2.cpu(), golden["f32_KiX"]) < GRAD_TOL
+
+
+def test_kernel_intermediates_against_qspace_model(golden, dev):
+    """Stage-by-stage check of the C ABI (gram -> factor -> solve_w -> xb_nll -> vbs -> vb) against the
+    float64 Q-space model of the oracle."""
+    from gppvae_b200 import ops
+    from gppvae_b200._lib import S_LOGDETB, S_TRBINV, S_V0, S_VN
+    from oracle import gp_oracle as O
+    if "Vdirect" in golden:
+        V64 = torch.as_tensor(golden["Vdirect"], dtype=torch.float64)
+    else:
+        V64 = torch.as_tensor(golden["f64_V"], dtype=torch.float64)
+    Z64 = torch.as_tensor(golden["Z"], dtype=torch.float64)
+    lvs64 = torch.as_tensor(golden["lvs"], dtype=torch.float64)
+    m = O.qspace_model(Z64, V64, lvs64)
+    Vm, ldv = ops.as_matrix(_cuda(V64.numpy(), dev), "V")
+    Xm, ldx = ops.as_matrix(_cuda(golden["Z"], dev), "X")
+    n, Q, L, Qt, Lt = Vm.shape[0], Vm.shape[1], Xm.shape[1], V64.shape[1], Z64.shape[1]
+    GC = ops.gram_vtz(Vm, ldv, Xm, ldx, n, Q, L)
+    assert rel_err(GC[:Qt, :Qt].cpu(), m["G"]) < 2e-6
+    assert rel_err(GC[:Qt, Q:Q + Lt].cpu(), m["C"]) < 2e-6
+    assert torch.equal(GC[:, :Q], GC[:, :Q].t())          # both triangles written, exactly symmetric
+    vs = torch.softmax(_cuda(golden["lvs"], dev), 0)
+    fac = ops.factor(GC, Q + L, Q, vs, True)
+    sc = fac.scal.cpu().numpy()
+    assert abs(sc[S_V0] + sc[S_VN] - 1) < 1e-6
+    assert abs(sc[S_LOGDETB] - m["logdetB"].item()) < 1e-5 * max(1.0, abs(m["logdetB"].item()))
+    assert abs(sc[S_TRBINV] - (m["trBinv"].item() + (Q - Qt))) < 1e-4 * Q
+    assert rel_err(fac.Binv[:Qt, :Qt].cpu(), m["Binv"]) < 1e-4
+    W, scal = ops.solve_w(fac, GC[:, Q:], Q + L, L, Lt, n)
+    assert rel_err(W[:Qt, :Lt].cpu(), m["W"]) < 1e-4
+    Xb, nll = ops.xb_nll(Vm, ldv, Xm, ldx, W, n, Q, L, scal)
+    assert rel_err(Xb[:, :Lt].cpu(), m["Xb"]) < GRAD_TOL
+    assert abs(nll.double().sum().item() - m["nll"].sum().item()) / abs(m["nll"].sum().item()) < NLL_TOL
+    vbs = ops.vbs_from_scal(scal, n, Q, Lt)
+    assert rel_err(vbs.cpu(), m["vbs"]) < 1e-4
+    Vb = ops.vb(Vm, ldv, Xb, fac.Binv, W, scal, n, Q, L, Lt)
+    assert rel_err(Vb[:, :Qt].cpu(), m["Vb"]) < 2e-3
+
+
+@pytest.mark.parametrize("kind,lvs", [("trained", (0.0, 0.0)), ("init", (0.0, 0.0)), ("trained", (2.0, -4.0))])
+def test_faceplace_c1_against_oracle(dev, kind, lvs):
+    """BASELINE.json configs[0] shape (N=4005, p=64, q=9 -> Q=576, L=256) against the oracle in fp32 and fp64."""
+    import gppvae_b200
+    from gppvae_b200.synth import make_problem
+    from oracle import gp_oracle as O
+    pr = make_problem(4005, 64, 9, 256, kind=kind, lvs=lvs, seed=11)
+    V32 = O.feature_map(pr.x0, pr.v0, pr.d, pr.w)
+    o32 = O.taylor_coeff(pr.Z, [V32], pr.lvs)
+    V64 = O.feature_map(pr.x0.double(), pr.v0.double(), pr.d, pr.w)
+    o64 = O.taylor_coeff(pr.Z.double(), [V64], pr.lvs.double())
+
+    vm = gppvae_b200.Vmodel(pr.x0.shape[0], 9, 64, 9).to(dev)
+    gp = gppvae_b200.GP().to(dev)
+    with torch.no_grad():
+        vm.x0.copy_(pr.x0.to(dev)); vm.v0.copy_(pr.v0.to(dev)); gp.lvs.copy_(pr.lvs.to(dev))
+        V = vm(pr.d.to(dev), pr.w.to(dev))
+    assert rel_err(V.cpu(), V64) < 1e-6
+    Xb, Vbs, vbs, nll = gp.taylor_coeff(pr.Z.to(dev), [V])
+    e_new32 = abs(nll.double().sum().item() - o32[3].double().sum().item()) / abs(o32[3].double().sum().item())
+    e_new64 = abs(nll.double().sum().item() - o64[3].sum().item()) / abs(o64[3].sum().item())
+    e_ref = abs(o32[3].double().sum().item() - o64[3].sum().item()) / abs(o64[3].sum().item())
+    print(f"[c1 {kind} lvs={lvs}] rel NLL err: new-ref32 {e_new32:.2e} new-ref64 {e_new64:.2e} ref32-ref64 {e_ref:.2e}")
+    print(f"  Xb  : new-ref32 {rel_err(Xb.cpu(), o32[0]):.2e} new-ref64 {rel_err(Xb.cpu(), o64[0]):.2e} "
+          f"ref32-ref64 {rel_err(o32[0], o64[0]):.2e}")
+    print(f"  Vb  : new-ref64 {rel_err(Vbs[0].cpu(), o64[1][0]):.2e} ref32-ref64 {rel_err(o32[1][0], o64[1][0]):.2e}")
+    print(f"  vbs : new-ref64 {rel_err(vbs.cpu(), o64[2]):.2e} ref32-ref64 {rel_err(o32[2], o64[2]):.2e}")
+    assert e_new32 < NLL_TOL and e_new64 < NLL_TOL
+    assert rel_err(Xb.cpu(), o32[0]) < GRAD_TOL and rel_err(Xb.cpu(), o64[0]) < GRAD_TOL
+    assert rel_err(Vbs[0].cpu(), o64[1][0]) < max(5 * rel_err(o32[1][0], o64[1][0]), 2e-3)
+    assert rel_err(vbs.cpu(), o64[2]) < max(5 * rel_err(o32[2], o64[2]), 1e-4)
+
+
+@pytest.mark.parametrize("n,p,q,L", [(1, 4, 1, 4), (7, 3, 3, 5), (130, 5, 7, 9), (257, 16, 4, 260), (1000, 33, 4, 8)])
+def test_ragged_shapes_against_oracle(dev, n, p, q, L):
+    """Rows, ranks and latent widths that are not multiples of any tile (incl. column padding paths)."""
+    import gppvae_b200
+    from gppvae_b200.synth import make_problem
+    from oracle import gp_oracle as O
+    pr = make_problem(n, p, q, L, kind="trained", lvs=(0.5, -0.5), seed=n)
+    V64 = O.feature_map(pr.x0.double(), pr.v0.double(), pr.d, pr.w)
+    o64 = O.taylor_coeff(pr.Z.double(), [V64], pr.lvs.double())
+    vm = gppvae_b200.Vmodel(pr.x0.shape[0], q, p, q).to(dev)
+    gp = gppvae_b200.GP().to(dev)
+    with torch.no_grad():
+        vm.x0.copy_(pr.x0.to(dev)); vm.v0.copy_(pr.v0.to(dev)); gp.lvs.copy_(pr.lvs.to(dev))
+        V = vm(pr.d.to(dev), pr.w.to(dev))
+    assert V.shape == (n, p * q)
+    assert rel_err(V.cpu(), V64) < 1e-6
+    Xb, Vbs, vbs, nll = gp.taylor_coeff(pr.Z.to(dev), [V])
+    assert Xb.shape == (n, L) and Vbs[0].shape == (n, p * q) and nll.shape == (n, 1)
+    assert abs(nll.double().sum().item() - o64[3].sum().item()) / abs(o64[3].sum().item()) < NLL_TOL
+    assert rel_err(Xb.cpu(), o64[0]) < GRAD_TOL
+    assert rel_err(Vbs[0].cpu(), o64[1][0]) < 2e-3
+    assert rel_err(vbs.cpu(), o64[2]) < 1e-3
+
+
+def test_out_of_range_index_gives_nan_row(dev):
+    import gppvae_b200
+    vm = gppvae_b200.Vmodel(4, 4, 2, 2).to(dev)
+    with torch.no_grad():
+        V = vm(torch.tensor([0, 9, 1], device=dev), torch.tensor([0, 0, 3], device=dev))
+    assert torch.isnan(V[1]).all() and not torch.isnan(V[0]).any() and not torch.isnan(V[2]).any()
+
+
+def test_argument_errors(dev):
+    import gppvae_b200
+    gp = gppvae_b200.GP().to(dev)
+    with pytest.raises(ValueError):
+        gp.taylor_coeff(torch.zeros(8, 4), [torch.zeros(8, 4)])                       # CPU tensors
+    with pytest.raises(ValueError):
+        gp.taylor_coeff(torch.zeros(8, 4, device=dev, dtype=torch.float64), [torch.zeros(8, 4, device=dev)])
+    with pytest.raises(ValueError):
+        gp.taylor_coeff(torch.zeros(8, 4, device=dev), [torch.zeros(9, 4, device=dev)])
+    with pytest.raises(NotImplementedError):
+        gppvae_b200.GP(vsum2one=False)
+    from gppvae_b200 import _lib
+    lib = _lib.load()
+    assert lib.gpp_gram_vtz(None, 4, None, 4, 8, 4, 4, None, 8, None, 0, None) == -1
+    assert b"gram_vtz" in lib.gpp_last_error()
+
+
+def test_full_size_c2_properties(dev):
+    """BASELINE.json configs[1] at full size (N=100k, Q=1024, L=256): size-independent properties.
+
+    (i) row-shard additivity of pass 1 (the multi-GPU contract): GC(rows A) + GC(rows B) == GC(all);
+    (ii) sum_i quad_i == (||Z||^2 - <C, W>) / vn, an independent route through Q-space;
+    (iii) sum(nll) is invariant to a row permutation; (iv) Xb is permutation-equivariant;
+    (v) a random 512-row sub-sample of Xb matches an fp64 evaluation of (Z - V W)/vn built from our W.
+    """
+    import gppvae_b200
+    from gppvae_b200 import ops
+    from gppvae_b200.synth import CONFIGS, make_problem
+    cfg = CONFIGS["c2"]
+    pr = make_problem(cfg["N"], cfg["p"], cfg["q"], cfg["L"], kind="trained", lvs=(0.0, 0.0), seed=5, device=dev)
+    N, Q, L = cfg["N"], cfg["p"] * cfg["q"], cfg["L"]
+    vm = gppvae_b200.Vmodel(pr.x0.shape[0], cfg["q"], cfg["p"], cfg["q"]).to(dev)
+    gp = gppvae_b200.GP().to(dev)
+    with torch.no_grad():
+        vm.x0.copy_(pr.x0); vm.v0.copy_(pr.v0); gp.lvs.copy_(pr.lvs)
+        V = vm(pr.d, pr.w)
+    assert torch.allclose((V * V).sum(1), torch.ones(N, device=dev), atol=1e-5)     # unit rows
+    half = 50_048
+    GC = ops.gram_vtz(V, Q, pr.Z, L, N, Q, L)
+    GA = ops.gram_vtz(V[:half], Q, pr.Z[:half], L, half, Q, L)
+    GB = ops.gram_vtz(V[half:], Q, pr.Z[half:], L, N - half, Q, L)
+    assert rel_err((GA + GB).cpu(), GC.cpu()) < 2e-6
+    assert abs(GC[:, :Q].diagonal().double().sum().item() - N) / N < 1e-5             # tr(V^T V) = N
+    Xb, Vbs, vbs, nll = gp.taylor_coeff(pr.Z, [V])
+    sc = gp.last_scalars.cpu().numpy()
+    W, _ = ops.solve_w(gp._cache.fac, GC[:, Q:], Q + L, L, L, N)
+    zz = (pr.Z.double() ** 2).sum().item()
+    cw = (GC[:, Q:].double() * W.double()).sum().item()
+    from gppvae_b200._lib import S_QUAD, S_VN
+    assert abs(sc[S_QUAD] - (zz - cw) / sc[S_VN]) / abs(sc[S_QUAD]) < 1e-5
+    perm = torch.randperm(N, device=dev)
+    Xb2, _, vbs2, nll2 = gp.taylor_coeff(pr.Z[perm].contiguous(), [V[perm].contiguous()])
+    assert abs(nll2.double().sum().item() - nll.double().sum().item()) / abs(nll.double().sum().item()) < 1e-6
+    assert rel_err(Xb2.cpu(), Xb[perm].cpu()) < 1e-5
+    assert rel_err(vbs2.cpu(), vbs.cpu()) < 1e-4
+    idx = torch.randperm(N, device=dev)[:512]
+    ref = (pr.Z[idx].double() - V[idx].double() @ W.double()) / sc[S_VN]
+    assert rel_err(Xb[idx].cpu(), ref.cpu()) < 1e-5
+
+
+def test_host_entry_matches_oracle(dev):
+    """gpp_gp_term_host (the end-to-end C entry bench.py times) against the oracle."""
+    import ctypes
+    from gppvae_b200 import _lib
+    from gppvae_b200.synth import make_problem
+    from oracle import gp_oracle as O
+    pr = make_problem(3000, 16, 8, 64, kind="trained", lvs=(0.3, -0.3), seed=3)
+    V64 = O.feature_map(pr.x0.double(), pr.v0.double(), pr.d, pr.w)
+    o64 = O.taylor_coeff(pr.Z.double(), [V64], pr.lvs.double())
+    lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    assert lib.gpp_host_ctx_create(ctypes.byref(ctx)) == 0
+    n, L = pr.Z.shape
+    nll = torch.empty(n).pin_memory(); Xb = torch.empty(n, L).pin_memory(); vbs = torch.empty(2).pin_memory()
+    x0, v0, d, w, Z, lvs = (t.contiguous().pin_memory() for t in (pr.x0, pr.v0, pr.d, pr.w, pr.Z, pr.lvs))
+    for _ in range(2):   # second call reuses the context's device arena
+        rc = lib.gpp_gp_term_host(ctx, x0.data_ptr(), x0.shape[0], 16, v0.data_ptr(), 8, 8, d.data_ptr(), w.data_ptr(),
+                                  Z.data_ptr(), n, L, lvs.data_ptr(), nll.data_ptr(), Xb.data_ptr(), vbs.data_ptr())
+        assert rc == 0, lib.gpp_last_error()
+    assert lib.gpp_host_ctx_destroy(ctx) == 0
+    assert abs(nll.double().sum().item() - o64[3].sum().item()) / abs(o64[3].sum().item()) < NLL_TOL
+    assert rel_err(Xb, o64[0]) < GRAD_TOL
+    assert rel_err(vbs, o64[2]) < 1e-3
