@@ -231,8 +231,11 @@ def test_faceplace_c1_against_oracle(dev, kind, lvs):
           f"ref32-ref64 {rel_err(o32[0], o64[0]):.2e}")
     print(f"  Vb  : new-ref64 {rel_err(Vbs[0].cpu(), o64[1][0]):.2e} ref32-ref64 {rel_err(o32[1][0], o64[1][0]):.2e}")
     print(f"  vbs : new-ref64 {rel_err(vbs.cpu(), o64[2]):.2e} ref32-ref64 {rel_err(o32[2], o64[2]):.2e}")
-    assert e_new32 < NLL_TOL and e_new64 < NLL_TOL
-    assert rel_err(Xb.cpu(), o32[0]) < GRAD_TOL and rel_err(Xb.cpu(), o64[0]) < GRAD_TOL
+    # Graded against fp64 ground truth; against the fp32 reference the bound is widened by that reference's
+    # own distance from fp64 (triangle inequality) -- at lvs=[2,-4] the fp32 reference itself is 1e-4 away.
+    assert e_new64 < NLL_TOL and e_new32 < NLL_TOL + e_ref
+    assert rel_err(Xb.cpu(), o64[0]) < GRAD_TOL
+    assert rel_err(Xb.cpu(), o32[0]) < GRAD_TOL + rel_err(o32[0], o64[0])
     assert rel_err(Vbs[0].cpu(), o64[1][0]) < max(5 * rel_err(o32[1][0], o64[1][0]), 2e-3)
     assert rel_err(vbs.cpu(), o64[2]) < max(5 * rel_err(o32[2], o64[2]), 1e-4)
 
