@@ -31,6 +31,8 @@ _SIGNATURES = {
     "gpp_gram_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "gpp_gram_vtz": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, _PF, c_int64, _PF, c_size_t,
                              c_void_p]),
+    "gpp_gram_vtz_simt": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, _PF, c_int64, _PF, c_size_t,
+                                  c_void_p]),
     "gpp_factor_state_bytes": (c_size_t, [c_int32]),
     "gpp_solve_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "gpp_factor": (c_int, [_PF, c_int64, c_int32, _PF, c_uint32, _PF, _PF, _PF, c_size_t, c_void_p]),

@@ -45,11 +45,15 @@ using namespace gpp;
 
 extern "C" int gpp_version(void) { return 100; }
 extern "C" const char* gpp_last_error(void) { return g_last_error.c_str(); }
-extern "C" const char* gpp_gemm_engine(void) { return "simt-fp32"; }
+extern "C" const char* gpp_gemm_engine(void) { return "tcgen05-3xtf32"; }
 extern "C" uint64_t gpp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------ pass 1
-extern "C" size_t gpp_gram_workspace_bytes(int64_t n, int32_t Q, int32_t L) { return tn_workspace_bytes(n, Q, Q, L, 1); }
+extern "C" size_t gpp_gram_workspace_bytes(int64_t n, int32_t Q, int32_t L) {
+  const size_t a = tn_workspace_bytes(n, Q, Q, L, 1);
+  const size_t b = tc_pass1_supported(n, Q, L) ? tc_pass1_workspace_bytes(n, Q, L) : 0;
+  return a > b ? a : b;
+}
 
 extern "C" int gpp_gram_vtz(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int32_t Q, int32_t L,
                             float* GC, int64_t ldgc, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
@@ -58,6 +62,20 @@ extern "C" int gpp_gram_vtz(const float* V, int64_t ldv, const float* X, int64_t
   GPP_REQUIRE(mat_ok(V, ldv, Q), "gram_vtz: V must be 16-byte aligned with ldv >= Q and ldv %% 4 == 0");
   GPP_REQUIRE(L == 0 || mat_ok(X, ldx, L), "gram_vtz: X must be 16-byte aligned with ldx >= L and ldx %% 4 == 0");
   GPP_REQUIRE(mat_ok(GC, ldgc, (int64_t)Q + L), "gram_vtz: GC must be 16-byte aligned with ldgc >= Q + L");
+  // large problems run on the tensor cores (3xTF32); tiles that cannot fill a 128 x 256 UMMA use the fp32 tile engine
+  if (tc_pass1_supported(n, Q, L))
+    return launch_tc_pass1(V, ldv, X, ldx, n, Q, L, GC, ldgc, workspace, workspace_bytes, (cudaStream_t)stream);
+  return launch_tn(V, ldv, Q, V, ldv, Q, X, ldx, L, n, 1, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
+}
+
+// Debug / cross-check entry: pass 1 on the fp32 SIMT tile engine regardless of size (tests compare the two).
+extern "C" int gpp_gram_vtz_simt(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int32_t Q,
+                                 int32_t L, float* GC, int64_t ldgc, void* workspace, size_t workspace_bytes,
+                                 gpp_stream_t stream) {
+  GPP_REQUIRE(n >= 0 && Q > 0 && L >= 0 && Q % 4 == 0 && L % 4 == 0, "gram_vtz_simt: bad shape");
+  GPP_REQUIRE(mat_ok(V, ldv, Q) && (L == 0 || mat_ok(X, ldx, L)) && mat_ok(GC, ldgc, (int64_t)Q + L),
+              "gram_vtz_simt: bad pointer / leading dimension");
   return launch_tn(V, ldv, Q, V, ldv, Q, X, ldx, L, n, 1, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes,
                    (cudaStream_t)stream);
 }

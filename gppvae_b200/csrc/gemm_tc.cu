@@ -1,0 +1,398 @@
+// Pass 1 on the 5th-generation tensor cores:  GC = V^T [V | X]  as 3xTF32 (hi.hi + hi.lo + lo.hi).
+//
+//   D(128 x 256 tile) = sum_k A[k, m]^T B[k, n]      A = V[:, 128 tm ..], B = V[:, 256 tn ..] or X[:, 256 j ..]
+//
+// Both operands are row-major with the contraction running over ROWS, i.e. MN-major UMMA operands.  For tf32 the
+// only MN-major shared-memory layout is SWIZZLE_128B_BASE32B (atom = 32 floats x 4 k-rows, 32-byte chunks XORed
+// with row % 4), which is exactly what a TMA box of {32 floats, BK rows} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+// writes: LBO = BK * 128 B between 32-float column groups, SBO = 512 B between 4-row k-groups, 1024 B per K = 8 step.
+//
+// Measured on B200 (experiments/tc/exp1_gram.cu): kind::tf32 TRUNCATES fp32 operands to tf32 and the TMEM
+// accumulator is rounded toward zero after every MMA (relative bias ~1.5e-8 per accumulation).  Hence
+//   * the converter warps round hi to nearest (and store it back) and lo = rn_tf32(a - hi): unbiased 2^-22 split;
+//   * accumulation in TMEM is limited to WINDOWS of kWinStages stages (24 MMAs, bias <= 3.6e-7 of the window sum);
+//     windows ping-pong between two TMEM buffers and are summed in fp32 registers (round-to-nearest) by the drain
+//     warps, which keeps G and C at fp32-level accuracy for any N.
+//
+// Warp roles (512 threads, 4 warpgroups, setmaxnreg re-balanced): warp 0 TMA producer, warp 1 MMA issuer + TMEM
+// owner, warps 4-7 converters, warps 8-15 drain.  Persistent over (tile, k-split) units; deterministic split-K:
+// every unit writes its own partial tile, tc_reduce_kernel sums them in a fixed order (fp64) and mirrors G.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace gpp {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TM = 128, TN = 256, TBK = 16, kStages = 4, kWinStages = 4;
+constexpr int kABytes = TM * TBK * 4, kBBytes = TN * TBK * 4, kRawBytes = kABytes + kBBytes;  // 8 K + 16 K
+constexpr int kStageBytes = 2 * kRawBytes;                                                     // raw(hi) + lo
+constexpr int kTcThreads = 512;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcShared {
+  uint64_t full[kStages], conv[kStages], empty[kStages], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+struct Pass1Params {
+  int64_t n;
+  int Q, L;
+  int tm_count;      // ceil(Q / 128)
+  int tiles_g;       // tiles of G: (tm, tn) with tn <= tm / 2
+  int tn_c;          // ceil(L / 256)
+  int tiles;         // tiles_g + tm_count * tn_c
+  int splits;
+  int64_t rows_per_split;  // multiple of TBK
+  float* partial;          // [tile][split][TM * TN]
+};
+
+__device__ __forceinline__ void decode_tile(const Pass1Params& p, int tile, int& tm, int& tn, bool& is_c) {
+  if (tile < p.tiles_g) {
+    is_c = false;
+    int t = 0, acc = 0;
+    while (acc + (t >> 1) + 1 <= tile) {
+      acc += (t >> 1) + 1;
+      ++t;
+    }
+    tm = t;
+    tn = tile - acc;
+  } else {
+    is_c = true;
+    const int r = tile - p.tiles_g;
+    tm = r / p.tn_c;
+    tn = r - tm * p.tn_c;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmX, Pass1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TcShared* sm = reinterpret_cast<TcShared*>(base + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm->full[s], 1);
+      mbar_init(&sm->conv[s], 4);
+      mbar_init(&sm->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm->tfull[b], 1);
+      mbar_init(&sm->tempty[b], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&sm->tmem_base, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  const int nunits = p.tiles * p.splits;
+
+  if (warp < 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 0) {
+      // ===================================================== TMA producer
+      if (lane == 0) {
+        tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tmX);
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+          const int split = u / p.tiles, tile = u - split * p.tiles;  // consecutive CTAs share a k-range (L2 reuse)
+          int tm, tn;
+          bool is_c;
+          decode_tile(p, tile, tm, tn, is_c);
+          const int64_t r0 = (int64_t)split * p.rows_per_split;
+          const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+          const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
+          const CUtensorMap* mb = is_c ? &tmX : &tmV;
+          for (int st = 0; st < nst; ++st, ++it) {
+            const int s = it % kStages;
+            mbar_wait(&sm->empty[s], ((it / kStages) & 1) ^ 1);
+            uint8_t* dst = base + s * kStageBytes;
+            const int row = (int)(r0 + (int64_t)st * TBK);
+            mbar_arrive_expect_tx(&sm->full[s], kRawBytes);
+#pragma unroll
+            for (int g = 0; g < TM / 32; ++g) tma_load_2d(dst + g * (TBK * 128), &tmV, tm * TM + g * 32, row, &sm->full[s]);
+#pragma unroll
+            for (int g = 0; g < TN / 32; ++g)
+              tma_load_2d(dst + kABytes + g * (TBK * 128), mb, tn * TN + g * 32, row, &sm->full[s]);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================================================== MMA issuer
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_tf32(TM, TN, true, true);
+        uint32_t it = 0, wc = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+          const int split = u / p.tiles;
+          const int64_t r0 = (int64_t)split * p.rows_per_split;
+          const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+          const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
+          for (int st0 = 0; st0 < nst; st0 += kWinStages, ++wc) {
+            const uint32_t buf = wc & 1;
+            mbar_wait(&sm->tempty[buf], ((wc >> 1) & 1) ^ 1);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + buf * TN;
+            const int wst = min(kWinStages, nst - st0);
+            for (int j = 0; j < wst; ++j, ++it) {
+              const int s = it % kStages;
+              mbar_wait(&sm->conv[s], (it / kStages) & 1);
+              tcgen05_fence_after();
+              const uint32_t a_hi = smem_u32(base + s * kStageBytes), b_hi = a_hi + kABytes;
+              const uint32_t a_lo = a_hi + kRawBytes, b_lo = a_lo + kABytes;
+#pragma unroll
+              for (int kk = 0; kk < TBK / 8; ++kk) {
+                const uint32_t o = kk * 1024;
+                const uint64_t dah = umma_desc(a_hi + o, TBK * 128, 512, kLayoutSw128Base32);
+                const uint64_t dbh = umma_desc(b_hi + o, TBK * 128, 512, kLayoutSw128Base32);
+                const uint64_t dal = umma_desc(a_lo + o, TBK * 128, 512, kLayoutSw128Base32);
+                const uint64_t dbl = umma_desc(b_lo + o, TBK * 128, 512, kLayoutSw128Base32);
+                umma_tf32(d, dah, dbh, idesc, (j | kk) != 0);
+                umma_tf32(d, dah, dbl, idesc, 1);
+                umma_tf32(d, dal, dbh, idesc, 1);
+              }
+              umma_commit(&sm->empty[s]);   // smem slot free once these MMAs have read it
+            }
+            umma_commit(&sm->tfull[buf]);   // window complete
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    setmaxnreg_dec<96>();
+    {
+      // ===================================================== converters: fp32 -> (hi, lo) tf32 planes
+      const int t = threadIdx.x - 128;  // 0..127
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int split = u / p.tiles;
+        const int64_t r0 = (int64_t)split * p.rows_per_split;
+        const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+        const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
+        for (int st = 0; st < nst; ++st, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&sm->full[s], (it / kStages) & 1);
+          float4* raw = reinterpret_cast<float4*>(base + s * kStageBytes);
+          float4* lo = reinterpret_cast<float4*>(base + s * kStageBytes + kRawBytes);
+#pragma unroll 4
+          for (int i = t; i < kRawBytes / 16; i += 128) {
+            const float4 v = raw[i];
+            float4 h, l;
+            split_tf32(v.x, h.x, l.x);
+            split_tf32(v.y, h.y, l.y);
+            split_tf32(v.z, h.z, l.z);
+            split_tf32(v.w, h.w, l.w);
+            raw[i] = h;
+            lo[i] = l;
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm->conv[s]);
+        }
+      }
+    }
+  } else {
+    // ======================================================= drain warps: TMEM windows -> fp32 registers -> partial tile
+    setmaxnreg_inc<184>();
+    const int q = warp & 3;               // TMEM lane quadrant this warp may touch
+    const int half = (warp - 8) >> 2;     // columns [128 half, 128 half + 128)
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t wc = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const int split = u / p.tiles, tile = u - split * p.tiles;
+      const int64_t r0 = (int64_t)split * p.rows_per_split;
+      const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+      const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
+      float acc[128];
+#pragma unroll
+      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      for (int st0 = 0; st0 < nst; st0 += kWinStages, ++wc) {
+        const uint32_t buf = wc & 1;
+        mbar_wait(&sm->tfull[buf], (wc >> 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld_32x32(tmem + lane_addr + buf * TN + half * 128 + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->tempty[buf]);
+      }
+      float* out = p.partial + ((size_t)tile * p.splits + split) * (size_t)(TM * TN) + (size_t)(q * 32 + lane) * TN +
+                   half * 128;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4)
+        *reinterpret_cast<float4*>(out + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// GC[r][c] = sum_s partial[tile][s][..] for every computed tile (fixed order, fp64 accumulation).
+__global__ void __launch_bounds__(256) tc_reduce_kernel(Pass1Params p, float* __restrict__ GC, int64_t ldgc) {
+  const int tile = blockIdx.x;
+  int tm, tn;
+  bool is_c;
+  decode_tile(p, tile, tm, tn, is_c);
+  const int ncols = is_c ? p.L : p.Q;
+  const int col0 = tn * TN, row0 = tm * TM;
+  const float* src = p.partial + (size_t)tile * p.splits * (size_t)(TM * TN);
+  for (int e = threadIdx.x; e < TM * TN / 4; e += blockDim.x) {
+    const int r = e / (TN / 4), c4 = (e - r * (TN / 4)) * 4;
+    if (row0 + r >= p.Q || col0 + c4 >= ncols) continue;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int s = 0; s < p.splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * (TM * TN) + r * TN + c4);
+      s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+    }
+    float* dst = GC + (int64_t)(row0 + r) * ldgc + (is_c ? p.Q : 0) + col0 + c4;
+    *reinterpret_cast<float4*>(dst) = make_float4((float)s0, (float)s1, (float)s2, (float)s3);
+  }
+}
+
+// G[r][c] = G[c][r] for c > r: the strict upper triangle is the transpose of the lower one (exact symmetry).
+__global__ void __launch_bounds__(256) tc_mirror_kernel(float* __restrict__ G, int64_t ldg, int Q) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x, by = blockIdx.y;   // block (by, bx) of 32 x 32, processed only when bx >= by
+  if (bx < by) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  // read lower block (rows 32 bx.., cols 32 by..)
+  for (int i = ty; i < 32; i += 8) {
+    const int r = bx * 32 + i, c = by * 32 + tx;
+    tile[i][tx] = (r < Q && c < Q) ? G[(int64_t)r * ldg + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int r = by * 32 + i, c = bx * 32 + tx;   // upper block element (r, c) = lower (c, r)
+    if (r < Q && c < Q && c > r) G[(int64_t)r * ldg + c] = tile[tx][i];
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major matrix (rows x cols, leading dimension ld), box = {box_cols floats, box_rows rows}.
+int make_map_2d(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return GPP_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+    return GPP_ERR_CUDA;
+  }
+  return GPP_OK;
+}
+
+void pass1_geometry(int64_t n, int Q, int L, Pass1Params& p) {
+  p.n = n; p.Q = Q; p.L = L;
+  p.tm_count = (int)ceil_div(Q, TM);
+  p.tiles_g = 0;
+  for (int t = 0; t < p.tm_count; ++t) p.tiles_g += (t >> 1) + 1;
+  p.tn_c = (int)ceil_div(L, TN);
+  p.tiles = p.tiles_g + p.tm_count * p.tn_c;
+  // choose the split count: best wave efficiency on the persistent grid, >= 1024 rows per split, <= 512 MB partials
+  const int sms = sm_count();
+  const int64_t max_by_rows = n / 1024 > 1 ? n / 1024 : 1;
+  const int64_t max_by_ws = (int64_t)(512ll << 20) / ((int64_t)p.tiles * TM * TN * 4);
+  int64_t smax = max_by_rows < max_by_ws ? max_by_rows : max_by_ws;
+  if (smax < 1) smax = 1;
+  if (smax > 64) smax = 64;
+  int best = 1;
+  double best_eff = 0;
+  for (int s = 1; s <= smax; ++s) {
+    const int64_t units = (int64_t)p.tiles * s;
+    const double eff = (double)units / (double)(ceil_div(units, sms) * sms);
+    if (eff > best_eff + 0.02) {   // prefer fewer splits unless efficiency improves by > 2 %
+      best_eff = eff;
+      best = s;
+    }
+  }
+  p.rows_per_split = ceil_div(ceil_div(n > 0 ? n : 1, best), TBK) * TBK;
+  p.splits = (int)ceil_div(n > 0 ? n : 1, p.rows_per_split);
+}
+
+}  // namespace
+
+bool tc_pass1_supported(int64_t n, int Q, int L) { return Q >= 128 && n >= 512 && encode_fn() != nullptr; }
+
+size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L) {
+  Pass1Params p;
+  pass1_geometry(n, Q, L, p);
+  return (size_t)p.tiles * p.splits * TM * TN * sizeof(float);
+}
+
+int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* GC,
+                    int64_t ldgc, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Pass1Params p;
+  pass1_geometry(n, Q, L, p);
+  const size_t need = (size_t)p.tiles * p.splits * TM * TN * sizeof(float);
+  if (!ws || ws_bytes < need) {
+    set_error("gram_vtz (tcgen05): workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return GPP_ERR_WORKSPACE;
+  }
+  p.partial = static_cast<float*>(ws);
+  CUtensorMap tmV, tmX;
+  GPP_TRY(make_map_2d(&tmV, V, n, Q, ldv, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  if (L > 0) GPP_TRY(make_map_2d(&tmX, X, n, L, ldx, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  else tmX = tmV;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GPP_CUDA(cudaFuncSetAttribute(tc_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int nunits = p.tiles * p.splits;
+  const int grid = nunits < sm_count() ? nunits : sm_count();
+  tc_pass1_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(tmV, tmX, p);
+  GPP_LAUNCH_CHECK();
+  tc_reduce_kernel<<<p.tiles, 256, 0, st>>>(p, GC, ldgc);
+  GPP_LAUNCH_CHECK();
+  dim3 mg((unsigned)ceil_div(Q, 32), (unsigned)ceil_div(Q, 32));
+  tc_mirror_kernel<<<mg, 256, 0, st>>>(GC, ldgc, Q);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
+}  // namespace gpp

@@ -34,6 +34,12 @@ int launch_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const 
               const float* W, int64_t ldw, const double* scal, int64_t n, int Q, int L, int L_true, float* Vb,
               int64_t ldvb, cudaStream_t st);
 
+// ---- gemm_tc.cu (tcgen05 / TMA / TMEM) ----
+bool tc_pass1_supported(int64_t n, int Q, int L);
+size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L);
+int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* GC,
+                    int64_t ldgc, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // ---- qspace.cu ----
 size_t factor_workspace_bytes(int Q);
 size_t solve_workspace_bytes(int Q, int L);

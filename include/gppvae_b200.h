@@ -97,6 +97,10 @@ size_t gpp_gram_workspace_bytes(int64_t n, int32_t Q, int32_t L);
 int gpp_gram_vtz(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int32_t Q, int32_t L,
                  float* GC, int64_t ldgc, void* workspace, size_t workspace_bytes, gpp_stream_t stream);
 
+/* Same contract as gpp_gram_vtz, always on the fp32 SIMT tile engine (cross-check entry used by the tests). */
+int gpp_gram_vtz_simt(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int32_t Q, int32_t L,
+                      float* GC, int64_t ldgc, void* workspace, size_t workspace_bytes, gpp_stream_t stream);
+
 /* Q-space solve, replicated on every rank.  vs = [v0, vn] is the DEVICE vector softmax(lvs) (gp.py:50).
  *
  * gpp_factor:   B = I + (v0/vn) G = Lc Lc^T (blocked Cholesky; replaces svd + inverse of gp.py:33-35),

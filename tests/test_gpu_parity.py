@@ -258,7 +258,10 @@ def test_ragged_shapes_against_oracle(dev, n, p, q, L):
     assert rel_err(V.cpu(), V64) < 1e-6
     Xb, Vbs, vbs, nll = gp.taylor_coeff(pr.Z.to(dev), [V])
     assert Xb.shape == (n, L) and Vbs[0].shape == (n, p * q) and nll.shape == (n, 1)
-    assert abs(nll.double().sum().item() - o64[3].sum().item()) / abs(o64[3].sum().item()) < NLL_TOL
+    # tiny problems: the per-row values have mixed signs and sum(nll) can nearly cancel, so the error of the sum is
+    # measured against sum|nll_i| here (the strict |sum| form is used on the Face-Place-shaped cases above)
+    assert abs(nll.double().sum().item() - o64[3].sum().item()) / o64[3].abs().sum().item() < NLL_TOL
+    assert rel_err(nll.cpu(), o64[3]) < 10 * NLL_TOL
     assert rel_err(Xb.cpu(), o64[0]) < GRAD_TOL
     assert rel_err(Vbs[0].cpu(), o64[1][0]) < 2e-3
     assert rel_err(vbs.cpu(), o64[2]) < 1e-3
@@ -355,3 +358,29 @@ def test_host_entry_matches_oracle(dev):
     assert abs(nll.double().sum().item() - o64[3].sum().item()) / abs(o64[3].sum().item()) < NLL_TOL
     assert rel_err(Xb, o64[0]) < GRAD_TOL
     assert rel_err(vbs, o64[2]) < 1e-3
+
+
+@pytest.mark.parametrize("n,Q,L", [(5000, 128, 64), (4096, 256, 256), (7777, 384, 100), (20000, 1024, 256)])
+def test_tensor_core_pass1_against_fp64_and_simt(dev, n, Q, L):
+    """Pass 1 on tcgen05 (3xTF32, windowed TMEM accumulation) against float64 and against the fp32 SIMT engine."""
+    import ctypes
+    from gppvae_b200 import _lib, ops
+    lib = _lib.load()
+    torch.manual_seed(n)
+    V = torch.randn(n, Q, device=dev) * torch.rand(1, Q, device=dev)
+    V[:, : Q // 2] = V[:, : Q // 2].abs()           # a positive block: exposes accumulation bias
+    X, ldx = ops.as_matrix(torch.randn(n, L, device=dev), "X")
+    Lk = X.shape[1]
+    ref = V.double().t() @ torch.cat([V.double(), X.double()], 1)
+    GC = ops.gram_vtz(V, Q, X, ldx, n, Q, Lk)
+    GS = torch.empty_like(GC)
+    ws = torch.empty(lib.gpp_gram_workspace_bytes(n, Q, Lk), dtype=torch.uint8, device=dev)
+    _lib.check(lib.gpp_gram_vtz_simt(V.data_ptr(), Q, X.data_ptr(), ldx, n, Q, Lk, GS.data_ptr(), Q + Lk, ws.data_ptr(),
+                                     ws.numel(), torch.cuda.current_stream().cuda_stream), "gram_vtz_simt")
+    torch.cuda.synchronize()
+    e_tc, e_simt = rel_err(GC.cpu(), ref.cpu()), rel_err(GS.cpu(), ref.cpu())
+    scale = ref.abs().cpu()
+    worst = float(((GC.double().cpu() - ref.cpu()).abs() / (scale + 1e-3 * scale.max())).max())
+    print(f"[pass1 n={n} Q={Q} L={L}] max-rel err: tcgen05 {e_tc:.2e}  simt {e_simt:.2e}  worst elementwise {worst:.2e}")
+    assert e_tc < 1e-6 and e_simt < 1e-6
+    assert torch.equal(GC[:, :Q], GC[:, :Q].t())
