@@ -130,8 +130,9 @@ extern "C" int gpp_factor_solve(const float* GC, int64_t ldgc, int32_t Q, int32_
 
 // ------------------------------------------------------------------ pass 2
 extern "C" size_t gpp_xb_workspace_bytes(int64_t n, int32_t Q, int32_t L) {
-  (void)Q;
-  return xb_workspace_bytes(n, L);
+  const size_t a = xb_workspace_bytes(n, L);
+  const size_t b = tc_rows_supported(n, Q, L) ? tc_xb_workspace_bytes(n, L) : 0;
+  return a > b ? a : b;
 }
 
 extern "C" int gpp_xb_nll(const float* V, int64_t ldv, const float* X, int64_t ldx, const float* W, int64_t ldw,
@@ -141,6 +142,9 @@ extern "C" int gpp_xb_nll(const float* V, int64_t ldv, const float* X, int64_t l
   GPP_REQUIRE(mat_ok(V, ldv, Q) && mat_ok(X, ldx, L) && mat_ok(W, ldw, L) && mat_ok(Xb, ldxb, L),
               "xb_nll: bad pointer / leading dimension");
   GPP_REQUIRE(scal && nll, "xb_nll: null scal / nll");
+  if (tc_rows_supported(n, Q, L))
+    return launch_tc_xb(V, ldv, X, ldx, W, ldw, n, Q, L, scal, 0.f, Xb, ldxb, nll, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
   return launch_xb(V, ldv, X, ldx, W, ldw, n, Q, L, scal, 0.f, Xb, ldxb, nll, workspace, workspace_bytes,
                    (cudaStream_t)stream);
 }
@@ -151,6 +155,9 @@ extern "C" int gpp_x_minus_am(const float* X, int64_t ldx, const float* A, int64
   GPP_REQUIRE(n >= 0 && k > 0 && m > 0 && k % 4 == 0 && m % 4 == 0, "x_minus_am: bad shape");
   GPP_REQUIRE(mat_ok(X, ldx, m) && mat_ok(A, lda, k) && mat_ok(M, ldm, m) && mat_ok(out, ldo, m),
               "x_minus_am: bad pointer / leading dimension");
+  if (tc_rows_supported(n, k, m))
+    return launch_tc_xb(A, lda, X, ldx, M, ldm, n, k, m, nullptr, alpha, out, ldo, nullptr, nullptr, 0,
+                        (cudaStream_t)stream);
   return launch_xb(A, lda, X, ldx, M, ldm, n, k, m, nullptr, alpha, out, ldo, nullptr, nullptr, 0,
                    (cudaStream_t)stream);
 }
@@ -162,18 +169,19 @@ extern "C" int gpp_vbs(const double* scal, int64_t n_total, int32_t Q, int32_t L
 
 // ------------------------------------------------------------------ Vb
 extern "C" size_t gpp_vb_workspace_bytes(int64_t n, int32_t Q, int32_t L) {
-  (void)n; (void)Q; (void)L;
-  return 0;
+  return tc_rows_supported(n, Q + L, Q) ? tc_vb_workspace_bytes(Q, L) : 0;
 }
 
 extern "C" int gpp_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const float* Binv, const float* W,
                       int64_t ldw, const double* scal, int64_t n, int32_t Q, int32_t L, int32_t L_true, float* Vb,
                       int64_t ldvb, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   GPP_REQUIRE(n >= 0 && Q > 0 && L > 0 && Q % 4 == 0 && L % 4 == 0 && L_true > 0 && L_true <= L, "vb: bad shape");
   GPP_REQUIRE(mat_ok(V, ldv, Q) && mat_ok(Xb, ldxb, L) && mat_ok(W, ldw, L) && mat_ok(Vb, ldvb, Q) && Binv &&
                   aligned16(Binv) && scal,
               "vb: bad pointer / leading dimension");
+  if (tc_rows_supported(n, Q + L, Q))
+    return launch_tc_vb(V, ldv, Xb, ldxb, Binv, W, ldw, scal, n, Q, L, L_true, Vb, ldvb, workspace, workspace_bytes,
+                        (cudaStream_t)stream);
   return launch_vb(V, ldv, Xb, ldxb, Binv, Q, W, ldw, scal, n, Q, L, L_true, Vb, ldvb, (cudaStream_t)stream);
 }
 

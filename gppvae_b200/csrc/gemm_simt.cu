@@ -378,6 +378,13 @@ __global__ void __launch_bounds__(1024) xb_finalize_kernel(const float* __restri
   }
 }
 
+int launch_xb_finalize(const float* quad_part, int tiles_n, int64_t n, const double* xb2_part, int64_t nparts,
+                       double* scal, float* nll, cudaStream_t st) {
+  xb_finalize_kernel<<<1, 1024, 0, st>>>(quad_part, tiles_n, n, xb2_part, nparts, scal, nll);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
 size_t xb_workspace_bytes(int64_t n, int L) {
   const int64_t tiles_n = ceil_div(L, BN), tiles_m = ceil_div(n, BM);
   return align_up((size_t)tiles_n * n * sizeof(float), 256) + (size_t)tiles_m * tiles_n * sizeof(double);

@@ -285,6 +285,236 @@ __global__ void __launch_bounds__(256) tc_mirror_kernel(float* __restrict__ G, i
   }
 }
 
+// =====================================================================================================
+// Row GEMM on tcgen05:  D(128 rows x 256 cols) = sum_k [A1 | A2][row, k] * B[k, col]     (3xTF32, windowed)
+//   pass 2  : A1 = V, B = W            epilogue  Xb = (X - D) * inv_vn, row quad partials, sum Xb^2
+//   Vb      : A1 = V, A2 = Xb, B = [r L Binv ; -W^T]   epilogue  out = D
+//   generic : out = alpha * (X - A M)
+// A is K-major (row-major, contraction along columns): TMA box {16 floats, 128 rows} with SWIZZLE_64B, UMMA
+// layout SWIZZLE_64B, SBO = 512 B (8 rows x 64 B), +32 B per K = 8 step.  B is MN-major exactly as in pass 1.
+// Same pipeline, converter and window/drain machinery as tc_pass1_kernel.
+// =====================================================================================================
+struct RowsParams {
+  int64_t n;
+  int K1, K2;          // contraction lengths of A1 and A2 (K2 may be 0)
+  int ncols;           // columns of B / of the output
+  int col_tiles;       // ceil(ncols / 256)
+  int64_t row_tiles;   // ceil(n / 128)
+  // epilogue
+  int mode;            // 0: out = alpha * (X - D) (+ quad / xb2 partials when quad_part != nullptr); 1: out = D
+  const float* X; int64_t ldx;
+  float* out; int64_t ldo;
+  const double* scal;  // mode 0: alpha = 1 / scal[VN] when set, else alpha_host
+  float alpha_host;
+  float* quad_part;    // [col_tiles * 2][n]
+  double* xb2_part;    // [units * 8]
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, RowsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TcShared* sm = reinterpret_cast<TcShared*>(base + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm->full[s], 1);
+      mbar_init(&sm->conv[s], 4);
+      mbar_init(&sm->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm->tfull[b], 1);
+      mbar_init(&sm->tempty[b], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&sm->tmem_base, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  const int64_t nunits = p.row_tiles * p.col_tiles;
+  const int nst1 = (p.K1 + TBK - 1) / TBK, nst2 = (p.K2 + TBK - 1) / TBK;
+  const int nst = nst1 + nst2;
+
+  if (warp < 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 0) {
+      if (lane == 0) {
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmA2);
+        tma_prefetch_desc(&tmB);
+        uint32_t it = 0;
+        for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+          const int64_t rt = u / p.col_tiles;
+          const int ct = (int)(u - rt * p.col_tiles);
+          const int row = (int)(rt * TM);
+          for (int st = 0; st < nst; ++st, ++it) {
+            const int s = it % kStages;
+            mbar_wait(&sm->empty[s], ((it / kStages) & 1) ^ 1);
+            uint8_t* dst = base + s * kStageBytes;
+            mbar_arrive_expect_tx(&sm->full[s], kRawBytes);
+            int kb;   // row of B where this k-block starts
+            if (st < nst1) {
+              tma_load_2d(dst, &tmA1, st * TBK, row, &sm->full[s]);
+              kb = st * TBK;
+            } else {
+              tma_load_2d(dst, &tmA2, (st - nst1) * TBK, row, &sm->full[s]);
+              kb = p.K1 + (st - nst1) * TBK;
+            }
+#pragma unroll
+            for (int g = 0; g < TN / 32; ++g)
+              tma_load_2d(dst + kABytes + g * (TBK * 128), &tmB, ct * TN + g * 32, kb, &sm->full[s]);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_tf32(TM, TN, false, true);
+        uint32_t it = 0, wc = 0;
+        for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+          for (int st0 = 0; st0 < nst; st0 += kWinStages, ++wc) {
+            const uint32_t buf = wc & 1;
+            mbar_wait(&sm->tempty[buf], ((wc >> 1) & 1) ^ 1);
+            tcgen05_fence_after();
+            const uint32_t d = tmem + buf * TN;
+            const int wst = min(kWinStages, nst - st0);
+            for (int j = 0; j < wst; ++j, ++it) {
+              const int s = it % kStages;
+              mbar_wait(&sm->conv[s], (it / kStages) & 1);
+              tcgen05_fence_after();
+              const uint32_t a_hi = smem_u32(base + s * kStageBytes), b_hi = a_hi + kABytes;
+              const uint32_t a_lo = a_hi + kRawBytes, b_lo = a_lo + kABytes;
+#pragma unroll
+              for (int kk = 0; kk < TBK / 8; ++kk) {
+                const uint64_t dah = umma_desc(a_hi + kk * 32, 16, 512, kLayoutSw64);
+                const uint64_t dal = umma_desc(a_lo + kk * 32, 16, 512, kLayoutSw64);
+                const uint64_t dbh = umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
+                const uint64_t dbl = umma_desc(b_lo + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
+                umma_tf32(d, dah, dbh, idesc, (j | kk) != 0);
+                umma_tf32(d, dah, dbl, idesc, 1);
+                umma_tf32(d, dal, dbh, idesc, 1);
+              }
+              umma_commit(&sm->empty[s]);
+            }
+            umma_commit(&sm->tfull[buf]);
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    setmaxnreg_dec<96>();
+    const int t = threadIdx.x - 128;
+    uint32_t it = 0;
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+      for (int st = 0; st < nst; ++st, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&sm->full[s], (it / kStages) & 1);
+        float4* raw = reinterpret_cast<float4*>(base + s * kStageBytes);
+        float4* lo = reinterpret_cast<float4*>(base + s * kStageBytes + kRawBytes);
+#pragma unroll 4
+        for (int i = t; i < kRawBytes / 16; i += 128) {
+          const float4 v = raw[i];
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x);
+          split_tf32(v.y, h.y, l.y);
+          split_tf32(v.z, h.z, l.z);
+          split_tf32(v.w, h.w, l.w);
+          raw[i] = h;
+          lo[i] = l;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->conv[s]);
+      }
+    }
+  } else {
+    setmaxnreg_inc<184>();
+    const int q = warp & 3;
+    const int half = (warp - 8) >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t wc = 0;
+    float alpha = p.alpha_host;
+    if (p.mode == 0 && p.scal) alpha = (float)(1.0 / p.scal[GPP_S_VN]);
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const int64_t rt = u / p.col_tiles;
+      const int ct = (int)(u - rt * p.col_tiles);
+      float acc[128];
+#pragma unroll
+      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      for (int st0 = 0; st0 < nst; st0 += kWinStages, ++wc) {
+        const uint32_t buf = wc & 1;
+        mbar_wait(&sm->tfull[buf], (wc >> 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld_32x32(tmem + lane_addr + buf * TN + half * 128 + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->tempty[buf]);
+      }
+      // ---- epilogue for this unit
+      const int64_t row = rt * TM + q * 32 + lane;
+      const int col0 = ct * TN + half * 128;
+      float quad = 0.f, xb2 = 0.f;
+      if (row < p.n) {
+        if (p.mode == 0) {
+          const float* xr = p.X + row * p.ldx + col0;
+          float* orow = p.out + row * p.ldo + col0;
+#pragma unroll
+          for (int i = 0; i < 128; i += 4) {
+            if (col0 + i < p.ncols) {
+              const float4 x = *reinterpret_cast<const float4*>(xr + i);
+              float4 o;
+              o.x = (x.x - acc[i + 0]) * alpha;
+              o.y = (x.y - acc[i + 1]) * alpha;
+              o.z = (x.z - acc[i + 2]) * alpha;
+              o.w = (x.w - acc[i + 3]) * alpha;
+              *reinterpret_cast<float4*>(orow + i) = o;
+              quad = fmaf(x.x, o.x, quad); quad = fmaf(x.y, o.y, quad);
+              quad = fmaf(x.z, o.z, quad); quad = fmaf(x.w, o.w, quad);
+              xb2 = fmaf(o.x, o.x, xb2); xb2 = fmaf(o.y, o.y, xb2);
+              xb2 = fmaf(o.z, o.z, xb2); xb2 = fmaf(o.w, o.w, xb2);
+            }
+          }
+          if (p.quad_part) p.quad_part[(int64_t)(ct * 2 + half) * p.n + row] = quad;
+        } else {
+          float* orow = p.out + row * p.ldo + col0;
+#pragma unroll
+          for (int i = 0; i < 128; i += 4)
+            if (col0 + i < p.ncols)
+              *reinterpret_cast<float4*>(orow + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+        }
+      }
+      if (p.mode == 0 && p.xb2_part) {
+        const float s = warp_sum(xb2);
+        if (lane == 0) p.xb2_part[u * 8 + (warp - 8)] = (double)s;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// Bstk (Q + L rows, Q cols) = [ (v0/vn) L_true Binv ; -W^T ]
+__global__ void __launch_bounds__(256) build_bstk_kernel(const float* __restrict__ Binv, const float* __restrict__ W,
+                                                         int64_t ldw, const double* __restrict__ scal, int Q, int L,
+                                                         int L_true, float* __restrict__ Bstk) {
+  const float coef = (float)(scal[GPP_S_V0] / scal[GPP_S_VN] * (double)L_true);
+  const int64_t total = (int64_t)(Q + L) * Q;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / Q), c = (int)(e - (int64_t)r * Q);
+    Bstk[e] = r < Q ? coef * Binv[(int64_t)r * Q + c] : -W[(int64_t)c * ldw + (r - Q)];
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -393,6 +623,75 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
   tc_mirror_kernel<<<mg, 256, 0, st>>>(GC, ldgc, Q);
   GPP_LAUNCH_CHECK();
   return GPP_OK;
+}
+
+bool tc_rows_supported(int64_t n, int K, int ncols) { return n >= 512 && K >= 64 && ncols >= 64 && encode_fn() != nullptr; }
+
+size_t tc_xb_workspace_bytes(int64_t n, int L) {
+  const int64_t col_tiles = ceil_div(L, TN), row_tiles = ceil_div(n, TM);
+  return align_up((size_t)col_tiles * 2 * n * sizeof(float), 256) + (size_t)row_tiles * col_tiles * 8 * sizeof(double);
+}
+
+static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, int64_t lda2, int K2, const float* B,
+                       int64_t ldb, int64_t n, int ncols, RowsParams& p, cudaStream_t st) {
+  CUtensorMap tmA1, tmA2, tmB;
+  GPP_TRY(make_map_2d(&tmA1, A1, n, K1, lda1, TBK, TM, CU_TENSOR_MAP_SWIZZLE_64B));
+  if (K2 > 0) GPP_TRY(make_map_2d(&tmA2, A2, n, K2, lda2, TBK, TM, CU_TENSOR_MAP_SWIZZLE_64B));
+  else tmA2 = tmA1;
+  GPP_TRY(make_map_2d(&tmB, B, (int64_t)K1 + K2, ncols, ldb, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  p.n = n; p.K1 = K1; p.K2 = K2; p.ncols = ncols;
+  p.col_tiles = (int)ceil_div(ncols, TN);
+  p.row_tiles = ceil_div(n, TM);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GPP_CUDA(cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int64_t nunits = p.row_tiles * p.col_tiles;
+  const int grid = (int)(nunits < sm_count() ? nunits : sm_count());
+  if (grid <= 0) return GPP_OK;
+  tc_rows_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(tmA1, tmA2, tmB, p);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
+// out = alpha (X - A M); with nll != nullptr also the NLL epilogue (quad partials -> xb_finalize).
+int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n,
+                 int Q, int L, double* scal, float alpha_host, float* Xb, int64_t ldxb, float* nll, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+  RowsParams p{};
+  p.mode = 0; p.X = X; p.ldx = ldx; p.out = Xb; p.ldo = ldxb; p.scal = scal; p.alpha_host = alpha_host;
+  const int64_t col_tiles = ceil_div(L, TN), row_tiles = ceil_div(n, TM);
+  if (nll) {
+    const size_t need = tc_xb_workspace_bytes(n, L);
+    if (!ws || ws_bytes < need) {
+      set_error("xb_nll (tcgen05): workspace too small (%zu < %zu bytes)", ws_bytes, need);
+      return GPP_ERR_WORKSPACE;
+    }
+    p.quad_part = static_cast<float*>(ws);
+    p.xb2_part = reinterpret_cast<double*>(static_cast<char*>(ws) + align_up((size_t)col_tiles * 2 * n * sizeof(float), 256));
+  }
+  GPP_TRY(launch_rows(V, ldv, Q, nullptr, 0, 0, W, ldw, n, L, p, st));
+  if (nll) GPP_TRY(launch_xb_finalize(p.quad_part, (int)(col_tiles * 2), n, p.xb2_part, row_tiles * col_tiles * 8, scal, nll, st));
+  return GPP_OK;
+}
+
+size_t tc_vb_workspace_bytes(int Q, int L) { return (size_t)(Q + L) * Q * sizeof(float); }
+
+int launch_tc_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const float* Binv, const float* W,
+                 int64_t ldw, const double* scal, int64_t n, int Q, int L, int L_true, float* Vb, int64_t ldvb, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+  const size_t need = tc_vb_workspace_bytes(Q, L);
+  if (!ws || ws_bytes < need) {
+    set_error("vb (tcgen05): workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return GPP_ERR_WORKSPACE;
+  }
+  float* Bstk = static_cast<float*>(ws);
+  build_bstk_kernel<<<1024, 256, 0, st>>>(Binv, W, ldw, scal, Q, L, L_true, Bstk);
+  GPP_LAUNCH_CHECK();
+  RowsParams p{};
+  p.mode = 1; p.out = Vb; p.ldo = ldvb;
+  return launch_rows(V, ldv, Q, Xb, ldxb, L, Bstk, Q, n, Q, p, st);
 }
 
 }  // namespace gpp

@@ -40,6 +40,19 @@ size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L);
 int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* GC,
                     int64_t ldgc, void* ws, size_t ws_bytes, cudaStream_t st);
 
+bool tc_rows_supported(int64_t n, int K, int ncols);
+size_t tc_xb_workspace_bytes(int64_t n, int L);
+int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n,
+                 int Q, int L, double* scal, float alpha_host, float* Xb, int64_t ldxb, float* nll, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
+size_t tc_vb_workspace_bytes(int Q, int L);
+int launch_tc_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const float* Binv, const float* W,
+                 int64_t ldw, const double* scal, int64_t n, int Q, int L, int L_true, float* Vb, int64_t ldvb, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
+// gemm_simt.cu: nll_i = 0.5 sum_t quad_part[t][i] + ROWCONST; scal[XB2], scal[QUAD]
+int launch_xb_finalize(const float* quad_part, int tiles_n, int64_t n, const double* xb2_part, int64_t nparts,
+                       double* scal, float* nll, cudaStream_t st);
+
 // ---- qspace.cu ----
 size_t factor_workspace_bytes(int Q);
 size_t solve_workspace_bytes(int Q, int L);

@@ -97,7 +97,7 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 //   bits [32,46) stride-dimension byte offset >> 4   bits [46,48) version = 1   bits [61,64) layout type
 // Layout types: 0 none, 1 SWIZZLE_128B_BASE32B (128-byte rows, 32-byte chunks XOR (row % 4); the ONLY layout for
 // MN-major tf32 operands: atom = 32 floats x 4 k-rows), 2 SWIZZLE_128B (16-byte chunks XOR (row % 8)), 4 64B, 6 32B.
-constexpr uint32_t kLayoutSw128Base32 = 1, kLayoutSw128 = 2;
+constexpr uint32_t kLayoutSw128Base32 = 1, kLayoutSw128 = 2, kLayoutSw64 = 4;
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                               uint32_t layout_type) {
   uint64_t d = 0;

@@ -187,9 +187,11 @@ def vbs_from_scal(scal: torch.Tensor, n_total: int, Q: int, L: int) -> torch.Ten
 
 
 def vb(V, ldv, Xb, Binv, W, scal, n, Q, L, L_true) -> torch.Tensor:
+    lib = _lib.load()
     Vb = torch.empty(n, Q, device=V.device, dtype=torch.float32)
-    check(_lib.load().gpp_vb(_p(V), ldv, _p(Xb), Xb.stride(0), _p(Binv), _p(W), W.stride(0), _p(scal), n, Q, L,
-                             L_true, _p(Vb), Q, None, 0, _stream()), "vb")
+    ws = _workspace(lib.gpp_vb_workspace_bytes(n, Q, L), V.device)
+    check(lib.gpp_vb(_p(V), ldv, _p(Xb), Xb.stride(0), _p(Binv), _p(W), W.stride(0), _p(scal), n, Q, L,
+                     L_true, _p(Vb), Q, _p(ws), ws.numel(), _stream()), "vb")
     return Vb
 
 

@@ -53,13 +53,19 @@ def make_problem(N: int, p: int, q: int, L: int, kind: str = "trained", lvs=(0.0
     mix = torch.randn(p * q, L, generator=gen, device=device)
     xn = x0 / x0.norm(dim=1, keepdim=True)
     wn = v0 / v0.norm(dim=1, keepdim=True)
-    gen_rows = torch.Generator(device=device).manual_seed(seed * 1000003 + 17 + row_offset)
+    # The noise is drawn in fixed chunks of global rows, each from its own seeded stream, so a row shard sees exactly
+    # the rows the unsharded problem has (multi-GPU runs are comparable with the 1-GPU run).
+    CH = 1 << 16
     Z = torch.empty(n_rows, L, device=device)
-    step = max(1, min(n_rows, (1 << 28) // max(p * q, 1)))
-    for s in range(0, n_rows, step):
-        e = min(n_rows, s + step)
+    for c in range(row_offset // CH, (row_offset + n_rows + CH - 1) // CH if n_rows else 0):
+        g0, g1 = max(c * CH, row_offset), min((c + 1) * CH, row_offset + n_rows, N)
+        if g1 <= g0:
+            continue
+        gen_c = torch.Generator(device=device).manual_seed(seed * 1000003 + 17 + c)
+        noise = torch.randn(min(CH, N - c * CH), L, generator=gen_c, device=device)[g0 - c * CH:g1 - c * CH]
+        s, e = g0 - row_offset, g1 - row_offset
         Vc = (xn[d[s:e]].unsqueeze(2) * wn[w[s:e]].unsqueeze(1)).reshape(e - s, -1)
-        Z[s:e] = 0.5 * torch.randn(e - s, L, generator=gen_rows, device=device) + Vc @ mix
+        Z[s:e] = 0.5 * noise + Vc @ mix
     return Problem(x0, v0, d, w, Z, torch.tensor(lvs, dtype=torch.float32, device=device),
                    dict(N=N, p=p, q=q, Q=p * q, L=L, kind=kind, lvs=list(lvs), seed=seed,
                         row_offset=row_offset, n_rows=n_rows))

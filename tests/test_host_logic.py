@@ -137,6 +137,10 @@ def test_synth_generator_is_seeded_and_shardable():
     assert torch.equal(a.Z, b.Z) and torch.equal(a.d, b.d)
     s = make_problem(200, 4, 5, 8, seed=3, row_offset=120, n_rows=80)
     assert torch.equal(s.d, a.d[120:]) and torch.equal(s.w, a.w[120:]) and torch.equal(s.x0, a.x0)
+    assert torch.equal(s.Z, a.Z[120:])          # a shard regenerates exactly its rows of the unsharded problem
+    big = make_problem(70000, 2, 2, 4, seed=1)
+    part = make_problem(70000, 2, 2, 4, seed=1, row_offset=65000, n_rows=5000)   # straddles a noise chunk boundary
+    assert torch.equal(part.Z, big.Z[65000:])
     assert int(a.d.max()) < a.x0.shape[0] and int(a.w.max()) < 5
     # every (object, view) pair appears at most once: "every object seen in every view" under a permutation
     assert len({(int(x), int(y)) for x, y in zip(a.d, a.w)}) == 200
