@@ -277,7 +277,13 @@ def run_ours(args):
     ms_e2e, _ = timed(e2e_step, args.steps, 1)
     h2d = hd.numel() * 8 + hw.numel() * 8 + hZ.numel() * 4
     d2h = h_nll.numel() * 4 + h_Xb.numel() * 4 + 8
-    nll_mean = float(h_nll.double().mean())
+    # checksum of the result over ALL ranks (comparable across --gpus: the synthetic rows do not depend on sharding)
+    chk = torch.stack([h_nll.double().sum(), h_Xb.double().pow(2).sum()]).to(dev)
+    if world > 1:
+        dist.all_reduce(chk)
+    nll_mean = float(chk[0]) / N
+    xb_sq = float(chk[1])
+    vbs_host = [float(v) for v in h_vbs]
 
     # ---- pure C entry with host buffers (1 GPU only): the same pipeline without Python between the calls
     ms_c = None
@@ -330,7 +336,7 @@ def run_ours(args):
                      "peak_source": f"{pk['source']} bf16_tflops_sustained / 2 (dense TF32), k=1 algorithmic flops",
                      "algorithmic_flops_per_launch": flops_pass1, "ms_per_launch": t_pass1,
                      "whole_step_frac_of_roofline": t_roof / ms, "whole_step_roofline_ms": t_roof},
-        "stage_ms": stage_ms, "nll_mean": nll_mean,
+        "stage_ms": stage_ms, "nll_mean": nll_mean, "xb_sumsq": xb_sq, "vbs": vbs_host,
         "full_taylor_coeff": None if ms_full is None else {"ms_per_step": ms_full, "value": N / (ms_full * 1e-3)},
     }
     if world == 1 and not args.skip_cpu:

@@ -9,7 +9,10 @@
 //
 // Measured on B200 (experiments/tc/exp1_gram.cu): kind::tf32 TRUNCATES fp32 operands to tf32 and the TMEM
 // accumulator is rounded toward zero after every MMA (relative bias ~1.5e-8 per accumulation).  Hence
-//   * the converter warps round hi to nearest (and store it back) and lo = rn_tf32(a - hi): unbiased 2^-22 split;
+//   * the raw fp32 tile is the hi operand as it stands (the hardware truncation IS the split) and the converter
+//     warps only write lo = rn_tf32(a - trunc_tf32(a)); measured against the variant that rounds hi to nearest and
+//     stores it back: same error (5-7e-7 of max|G|, no measurable bias) and 10 % faster (less shared-memory traffic,
+//     which is what bounds this kernel);
 //   * accumulation in TMEM is limited to WINDOWS of kWinStages stages (24 MMAs, bias <= 3.6e-7 of the window sum);
 //     windows ping-pong between two TMEM buffers and are summed in fp32 registers (round-to-nearest) by the drain
 //     warps, which keeps G and C at fp32-level accuracy for any N.
@@ -27,7 +30,13 @@ using namespace tc;
 
 namespace {
 
-constexpr int TM = 128, TN = 256, TBK = 16, kStages = 4, kWinStages = 4;
+#ifndef GPP_TC_WIN
+#define GPP_TC_WIN 4
+#endif
+#ifndef GPP_TC_STORE_HI
+#define GPP_TC_STORE_HI 0   // 0: raw fp32 is the hi operand (kind::tf32 truncates it in hardware); 1: hi = rn_tf32(a) written back
+#endif
+constexpr int TM = 128, TN = 256, TBK = 16, kStages = 4, kWinStages = GPP_TC_WIN;
 constexpr int kABytes = TM * TBK * 4, kBBytes = TN * TBK * 4, kRawBytes = kABytes + kBBytes;  // 8 K + 16 K
 constexpr int kStageBytes = 2 * kRawBytes;                                                     // raw(hi) + lo
 constexpr int kTcThreads = 512;
@@ -189,12 +198,20 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
 #pragma unroll 4
           for (int i = t; i < kRawBytes / 16; i += 128) {
             const float4 v = raw[i];
-            float4 h, l;
+            float4 l;
+#if GPP_TC_STORE_HI
+            float4 h;
             split_tf32(v.x, h.x, l.x);
             split_tf32(v.y, h.y, l.y);
             split_tf32(v.z, h.z, l.z);
             split_tf32(v.w, h.w, l.w);
             raw[i] = h;
+#else
+            l.x = tf32_rn(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+            l.y = tf32_rn(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+            l.z = tf32_rn(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+            l.w = tf32_rn(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+#endif
             lo[i] = l;
           }
           fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -417,12 +434,20 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll 4
         for (int i = t; i < kRawBytes / 16; i += 128) {
           const float4 v = raw[i];
-          float4 h, l;
+          float4 l;
+#if GPP_TC_STORE_HI
+          float4 h;
           split_tf32(v.x, h.x, l.x);
           split_tf32(v.y, h.y, l.y);
           split_tf32(v.z, h.z, l.z);
           split_tf32(v.w, h.w, l.w);
           raw[i] = h;
+#else
+          l.x = tf32_rn(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+          l.y = tf32_rn(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+          l.z = tf32_rn(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+          l.w = tf32_rn(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+#endif
           lo[i] = l;
         }
         fence_proxy_async_smem();

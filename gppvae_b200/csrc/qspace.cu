@@ -45,66 +45,125 @@ __global__ void __launch_bounds__(256) build_b_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------ diagonal block: factor + invert
-// One CTA of 64 threads; thread i owns row i of the 64 x 64 block in registers.
-// On exit A holds L (lower, zeros above) and Dinv holds L^-1 (lower, zeros above).
-__global__ void __launch_bounds__(NB) potf2_inv_kernel(float* __restrict__ A, int64_t lda, float* __restrict__ Dinv,
-                                                       int64_t ldd) {
-  __shared__ float Ls[NB][NB + 1];
+// One CTA of 256 threads on a 64 x 64 SPD block in shared memory, blocked 4 x 4 in 16 x 16 sub-blocks so that the
+// 64 sequential column steps run warp-synchronously (shuffles, no block barrier) and only 4 x 4 block barriers
+// remain:  per block column kb:  warp 0 factors the 16 x 16 diagonal block and inverts it in registers;
+//          all warps then do the 16-wide TRSM (as a multiply by that inverse) and the rank-16 trailing update.
+// The 64 x 64 inverse is assembled from the four 16 x 16 inverses by two recursive-doubling levels
+// (inv([[A,0],[C,D]]) = [[Ai,0],[-Di C Ai, Di]]).  On exit A holds L (lower, zeros above), Dinv holds L^-1.
+// (History: v1 unrolled everything over registers -- 400 KB of code, ~50 us per panel, instruction-fetch bound;
+//  v2 used rank-1 updates in shared memory with a barrier per column -- 48 us.)
+constexpr int kPotfThreads = 256;
+constexpr int SB = 16;
+__global__ void __launch_bounds__(kPotfThreads) potf2_inv_kernel(float* __restrict__ A, int64_t lda,
+                                                                 float* __restrict__ Dinv, int64_t ldd) {
+  __shared__ float As[NB][NB + 1];
   __shared__ float Xs[NB][NB + 1];
-  __shared__ float colbuf[2][NB];
-  __shared__ float rdiag[NB];
-  const int i = threadIdx.x;
-  for (int r = 0; r < NB; ++r) Ls[r][i] = A[(int64_t)r * lda + i];
+  __shared__ float Ts[NB / 2][NB / 2 + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned full = 0xffffffffu;
+  for (int e = tid; e < NB * NB; e += kPotfThreads) {
+    const int r = e >> 6, c = e & 63;
+    As[r][c] = A[(int64_t)r * lda + c];
+    Xs[r][c] = 0.f;
+  }
   __syncthreads();
-  float a[NB];
-#pragma unroll
-  for (int c = 0; c < NB; ++c) a[c] = Ls[i][c];
 
-  // right-looking Cholesky, one barrier per column (colbuf is double buffered)
+  for (int kb = 0; kb < NB / SB; ++kb) {
+    const int o = kb * SB;
+    if (warp == 0) {
+      const int l = lane & 15;   // lanes 16..31 mirror lanes 0..15 so every shuffle source is valid
+      float d[SB];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    colbuf[j & 1][i] = a[j];
+      for (int c = 0; c < SB; ++c) d[c] = As[o + l][o + c];
+#pragma unroll
+      for (int jj = 0; jj < SB; ++jj) {
+        const float piv = __shfl_sync(full, d[jj], jj);
+        const float ljj = sqrtf(piv);
+        const float rinv = 1.f / ljj;
+        const float lij = (l == jj) ? ljj : d[jj] * rinv;
+        d[jj] = lij;
+#pragma unroll
+        for (int c = jj + 1; c < SB; ++c) d[c] = fmaf(-lij, __shfl_sync(full, lij, c), d[c]);
+      }
+      // column l of the inverse of this 16 x 16 factor, by forward substitution
+      float x[SB];
+#pragma unroll
+      for (int i2 = 0; i2 < SB; ++i2) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < i2; ++k) s = fmaf(__shfl_sync(full, d[k], i2), x[k], s);
+        const float lii = __shfl_sync(full, d[i2], i2);
+        x[i2] = ((i2 == l ? 1.f : 0.f) - s) / lii;
+      }
+      if (lane < SB) {
+#pragma unroll
+        for (int c = 0; c < SB; ++c) {
+          As[o + l][o + c] = (c <= l) ? d[c] : 0.f;
+          Xs[o + c][o + l] = x[c];
+        }
+      }
+    }
     __syncthreads();
-    const float piv = colbuf[j & 1][j];
-    const float dj = sqrtf(piv);
-    const float rinv = 1.f / dj;
-    const float lij = (i == j) ? dj : a[j] * rinv;
-    a[j] = lij;
-    if (i > j) {
+    if (kb == NB / SB - 1) break;
+    // 16-wide TRSM below the diagonal block: L[r][o + c] = sum_{k <= c} A[r][o + k] * Li[c][k]
+    const int r0 = o + SB, nrows = NB - r0;
+    float tv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = j + 1; c < NB; ++c) a[c] = fmaf(-lij, colbuf[j & 1][c] * rinv, a[c]);
+    for (int t = 0; t < 3; ++t) {
+      const int e = tid + t * kPotfThreads;
+      if (e < nrows * SB) {
+        const int r = r0 + (e >> 4), c = e & 15;
+        float s = 0.f;
+        for (int k = 0; k <= c; ++k) s = fmaf(As[r][o + k], Xs[o + c][o + k], s);
+        tv[t] = s;
+      }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 #pragma unroll
-  for (int c = 0; c < NB; ++c) {
-    Ls[i][c] = (c <= i) ? a[c] : 0.f;
-    if (c == i) rdiag[i] = 1.f / a[c];  // static register index: no local-memory spill of a[]
+    for (int t = 0; t < 3; ++t) {
+      const int e = tid + t * kPotfThreads;
+      if (e < nrows * SB) As[r0 + (e >> 4)][o + (e & 15)] = tv[t];
+    }
+    __syncthreads();
+    // rank-16 update of the trailing lower triangle
+    for (int e = tid; e < nrows * nrows; e += kPotfThreads) {
+      const int rr = e / nrows, cc = e - rr * nrows;
+      if (cc <= rr) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < SB; ++k) s = fmaf(As[r0 + rr][o + k], As[r0 + cc][o + k], s);
+        As[r0 + rr][r0 + cc] -= s;
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
-  // column i of X = L^-1 by forward substitution (all reads of Ls are warp-uniform broadcasts)
-  float x[NB];
-#pragma unroll
-  for (int r = 0; r < NB; ++r) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int k = 0; k < r; ++k) {
-      const float t = Ls[r][k] * x[k];
-      if ((k & 3) == 0) s0 += t;
-      else if ((k & 3) == 1) s1 += t;
-      else if ((k & 3) == 2) s2 += t;
-      else s3 += t;
+  // assemble the 64 x 64 inverse: levels b = 16, 32
+  for (int b = SB; b < NB; b *= 2) {
+    const int npairs = NB / (2 * b);
+    // T = C . Ai  (b x b per pair), C = As[p + b .., p ..], Ai = Xs[p .., p ..] lower triangular
+    for (int e = tid; e < npairs * b * b; e += kPotfThreads) {
+      const int pr = e / (b * b), rem = e - pr * b * b, r = rem / b, c = rem - r * b, p0 = pr * 2 * b;
+      float s = 0.f;
+      for (int k = c; k < b; ++k) s = fmaf(As[p0 + b + r][p0 + k], Xs[p0 + k][p0 + c], s);
+      Ts[pr * b + r][c] = s;
     }
-    const float rhs = (r == i) ? 1.f : 0.f;
-    x[r] = (rhs - ((s0 + s1) + (s2 + s3))) * rdiag[r];
+    __syncthreads();
+    // X = -Di . T,  Di = Xs[p + b .., p + b ..] lower triangular
+    for (int e = tid; e < npairs * b * b; e += kPotfThreads) {
+      const int pr = e / (b * b), rem = e - pr * b * b, r = rem / b, c = rem - r * b, p0 = pr * 2 * b;
+      float s = 0.f;
+      for (int k = 0; k <= r; ++k) s = fmaf(Xs[p0 + b + r][p0 + b + k], Ts[pr * b + k][c], s);
+      Xs[p0 + b + r][p0 + c] = -s;
+    }
+    __syncthreads();
   }
-#pragma unroll
-  for (int r = 0; r < NB; ++r) Xs[r][i] = (r >= i) ? x[r] : 0.f;
-  __syncthreads();
-  for (int r = 0; r < NB; ++r) {
-    A[(int64_t)r * lda + i] = Ls[r][i];
-    Dinv[(int64_t)r * ldd + i] = Xs[r][i];
+
+  for (int e = tid; e < NB * NB; e += kPotfThreads) {
+    const int r = e >> 6, c = e & 63;
+    A[(int64_t)r * lda + c] = (c <= r) ? As[r][c] : 0.f;
+    Dinv[(int64_t)r * ldd + c] = Xs[r][c];
   }
 }
 
@@ -266,7 +325,7 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
     const int k0 = j * NB;
     float* diag = Bm + (int64_t)k0 * (Qp + 1);
     float* dinv = Linv + (int64_t)k0 * (Qp + 1);
-    potf2_inv_kernel<<<1, NB, 0, st>>>(diag, Qp, dinv, Qp);
+    potf2_inv_kernel<<<1, kPotfThreads, 0, st>>>(diag, Qp, dinv, Qp);
     GPP_LAUNCH_CHECK();
     const int rem = Qp - k0 - NB;
     if (rem <= 0) break;
