@@ -44,127 +44,243 @@ __global__ void __launch_bounds__(256) build_b_kernel(const float* __restrict__ 
   }
 }
 
-// ------------------------------------------------------------------ diagonal block: factor + invert
-// One CTA of 256 threads on a 64 x 64 SPD block in shared memory, blocked 4 x 4 in 16 x 16 sub-blocks so that the
-// 64 sequential column steps run warp-synchronously (shuffles, no block barrier) and only 4 x 4 block barriers
-// remain:  per block column kb:  warp 0 factors the 16 x 16 diagonal block and inverts it in registers;
-//          all warps then do the 16-wide TRSM (as a multiply by that inverse) and the rank-16 trailing update.
-// The 64 x 64 inverse is assembled from the four 16 x 16 inverses by two recursive-doubling levels
-// (inv([[A,0],[C,D]]) = [[Ai,0],[-Di C Ai, Di]]).  On exit A holds L (lower, zeros above), Dinv holds L^-1.
-// (History: v1 unrolled everything over registers -- 400 KB of code, ~50 us per panel, instruction-fetch bound;
-//  v2 used rank-1 updates in shared memory with a barrier per column -- 48 us.)
+// ------------------------------------------------------------------ diagonal block: factor / invert / panel solve
+// A 64 x 64 SPD block lives in shared memory and is processed by one CTA of 256 threads, blocked 4 x 4 in 16 x 16
+// sub-blocks: the 64 sequential column steps run warp-synchronously inside warp 0 (shuffles, no block barrier) and
+// only a handful of block barriers per 16-column block remain.
+//   factor64   : As <- L (lower; strict upper part zeroed), 16-wide TRSM by substitution, rank-16 trailing updates
+//   invert64   : Xs <- L^-1 from the four 16 x 16 inverses and two recursive-doubling levels
+//   chol_panel_kernel : EVERY CTA factors the diagonal block redundantly (5-7 us of work, but it removes the separate
+//                potf2 launch and its 64 x 64 inverse from the critical path), CTA 0 stores L11, CTA b >= 1 solves
+//                X L11^T = A21 for its 64 rows by forward substitution (4 lanes per row, shuffle reduction).
+//   diag_inv_kernel   : after the factorisation, all 64 x 64 diagonal inverses in one batched launch.
+// (History: v1 unrolled everything over registers -- 400 KB of straight-line code, ~50 us per panel; v2 did rank-1
+//  updates in shared memory with a barrier per column -- 48 us; v3 = factor64 + invert64 in one CTA -- 39 us.)
 constexpr int kPotfThreads = 256;
 constexpr int SB = 16;
-__global__ void __launch_bounds__(kPotfThreads) potf2_inv_kernel(float* __restrict__ A, int64_t lda,
-                                                                 float* __restrict__ Dinv, int64_t ldd) {
-  __shared__ float As[NB][NB + 1];
-  __shared__ float Xs[NB][NB + 1];
-  __shared__ float Ts[NB / 2][NB / 2 + 1];
+constexpr int kPitch = NB + 4;   // 68: conflict-free for "4 lanes per row" access patterns
+
+struct Block64 {
+  float a[NB][kPitch];
+};
+
+// li16 (optional): receives the inverses of the four 16 x 16 diagonal factors, li16[kb][c][k] = (L_kb^-1)[c][k];
+// they are computed by warp 1 while the other warps do the TRSM / rank-16 phases of the same block column.
+__device__ __forceinline__ void factor64(Block64& As, float* rd16, float (*li16)[SB][SB + 1]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned full = 0xffffffffu;
-  for (int e = tid; e < NB * NB; e += kPotfThreads) {
-    const int r = e >> 6, c = e & 63;
-    As[r][c] = A[(int64_t)r * lda + c];
-    Xs[r][c] = 0.f;
-  }
-  __syncthreads();
-
   for (int kb = 0; kb < NB / SB; ++kb) {
     const int o = kb * SB;
     if (warp == 0) {
       const int l = lane & 15;   // lanes 16..31 mirror lanes 0..15 so every shuffle source is valid
       float d[SB];
 #pragma unroll
-      for (int c = 0; c < SB; ++c) d[c] = As[o + l][o + c];
+      for (int c = 0; c < SB; ++c) d[c] = As.a[o + l][o + c];
 #pragma unroll
       for (int jj = 0; jj < SB; ++jj) {
         const float piv = __shfl_sync(full, d[jj], jj);
-        const float ljj = sqrtf(piv);
-        const float rinv = 1.f / ljj;
+        float rinv = rsqrtf(piv);                              // MUFU estimate + one Newton step: ~1 ulp, and far
+        rinv = rinv * fmaf(-0.5f * piv * rinv, rinv, 1.5f);    // shorter than the IEEE sqrt + divide chain
+        const float ljj = piv * rinv;
         const float lij = (l == jj) ? ljj : d[jj] * rinv;
         d[jj] = lij;
+        if (lane == jj) rd16[jj] = rinv;
 #pragma unroll
         for (int c = jj + 1; c < SB; ++c) d[c] = fmaf(-lij, __shfl_sync(full, lij, c), d[c]);
       }
-      // column l of the inverse of this 16 x 16 factor, by forward substitution
-      float x[SB];
+      if (lane < SB) {
+#pragma unroll
+        for (int c = 0; c < SB; ++c) As.a[o + l][o + c] = (c <= l) ? d[c] : 0.f;
+      }
+    }
+    __syncthreads();
+    if (li16 != nullptr && warp == 1) {   // inverse of the 16 x 16 factor just finished (column l by forward substitution)
+      const int l = lane & 15;
+      float d[SB], x[SB];
+#pragma unroll
+      for (int c = 0; c < SB; ++c) d[c] = As.a[o + l][o + c];
 #pragma unroll
       for (int i2 = 0; i2 < SB; ++i2) {
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < i2; ++k) s = fmaf(__shfl_sync(full, d[k], i2), x[k], s);
-        const float lii = __shfl_sync(full, d[i2], i2);
-        x[i2] = ((i2 == l ? 1.f : 0.f) - s) / lii;
+        x[i2] = ((i2 == l ? 1.f : 0.f) - s) * __shfl_sync(full, rd16[i2 & 15], 0);
       }
       if (lane < SB) {
 #pragma unroll
-        for (int c = 0; c < SB; ++c) {
-          As[o + l][o + c] = (c <= l) ? d[c] : 0.f;
-          Xs[o + c][o + l] = x[c];
+        for (int c = 0; c < SB; ++c) li16[kb][c][l] = x[c];
+      }
+    }
+    if (kb == NB / SB - 1) break;
+    const int r0 = o + SB, nrows = NB - r0;
+    // rows below: x L11^T = a  ->  x_c = (a_c - sum_{k<c} x_k L[c][k]) / L[c][c]   (one thread per row)
+    if (tid >= 64 && tid < 64 + nrows) {   // (warps 2.., leaving warp 1 to the inverse)
+      const int r = r0 + tid - 64;
+      float x[SB];
+#pragma unroll
+      for (int c = 0; c < SB; ++c) {
+        float s = As.a[r][o + c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) s = fmaf(-x[k], As.a[o + c][o + k], s);
+        x[c] = s * rd16[c];
+      }
+#pragma unroll
+      for (int c = 0; c < SB; ++c) As.a[r][o + c] = x[c];
+    }
+    __syncthreads();
+    // rank-16 update of the trailing lower triangle: thread = (row rr, 4-way split of the columns)
+    {
+      const int rr = tid >> 2, sub = tid & 3;
+      if (rr < nrows) {
+        float lr[SB];
+#pragma unroll
+        for (int k = 0; k < SB; ++k) lr[k] = As.a[r0 + rr][o + k];
+        for (int cc = sub; cc <= rr; cc += 4) {
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < SB; ++k) s = fmaf(lr[k], As.a[r0 + cc][o + k], s);
+          As.a[r0 + rr][r0 + cc] -= s;
         }
       }
     }
     __syncthreads();
-    if (kb == NB / SB - 1) break;
-    // 16-wide TRSM below the diagonal block: L[r][o + c] = sum_{k <= c} A[r][o + k] * Li[c][k]
-    const int r0 = o + SB, nrows = NB - r0;
-    float tv[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const int e = tid + t * kPotfThreads;
-      if (e < nrows * SB) {
-        const int r = r0 + (e >> 4), c = e & 15;
-        float s = 0.f;
-        for (int k = 0; k <= c; ++k) s = fmaf(As[r][o + k], Xs[o + c][o + k], s);
-        tv[t] = s;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const int e = tid + t * kPotfThreads;
-      if (e < nrows * SB) As[r0 + (e >> 4)][o + (e & 15)] = tv[t];
-    }
-    __syncthreads();
-    // rank-16 update of the trailing lower triangle
-    for (int e = tid; e < nrows * nrows; e += kPotfThreads) {
-      const int rr = e / nrows, cc = e - rr * nrows;
-      if (cc <= rr) {
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < SB; ++k) s = fmaf(As[r0 + rr][o + k], As[r0 + cc][o + k], s);
-        As[r0 + rr][r0 + cc] -= s;
-      }
-    }
-    __syncthreads();
   }
+  // zero the strict upper triangle (the caller stores / reads the block as a dense lower-triangular matrix)
+  for (int e = tid; e < NB * NB; e += kPotfThreads) {
+    const int r = e >> 6, c = e & 63;
+    if (c > r) As.a[r][c] = 0.f;
+  }
+  __syncthreads();
+}
 
-  // assemble the 64 x 64 inverse: levels b = 16, 32
-  for (int b = SB; b < NB; b *= 2) {
-    const int npairs = NB / (2 * b);
-    // T = C . Ai  (b x b per pair), C = As[p + b .., p ..], Ai = Xs[p .., p ..] lower triangular
-    for (int e = tid; e < npairs * b * b; e += kPotfThreads) {
-      const int pr = e / (b * b), rem = e - pr * b * b, r = rem / b, c = rem - r * b, p0 = pr * 2 * b;
+// Xs <- As^-1 (As lower triangular, strict upper part zero).  Ts: scratch of at least 32 x 33 floats.
+__device__ __forceinline__ void invert64(const Block64& As, Block64& Xs, float (*Ts)[NB / 2 + 1]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned full = 0xffffffffu;
+  for (int e = tid; e < NB * NB; e += kPotfThreads) Xs.a[e >> 6][e & 63] = 0.f;
+  __syncthreads();
+  if (warp < NB / SB) {   // warp w inverts diagonal sub-block w: lane l computes column l by forward substitution
+    const int o = warp * SB, l = lane & 15;
+    float d[SB], x[SB];
+#pragma unroll
+    for (int c = 0; c < SB; ++c) d[c] = As.a[o + l][o + c];   // row l of the 16 x 16 factor
+#pragma unroll
+    for (int i2 = 0; i2 < SB; ++i2) {
       float s = 0.f;
-      for (int k = c; k < b; ++k) s = fmaf(As[p0 + b + r][p0 + k], Xs[p0 + k][p0 + c], s);
+#pragma unroll
+      for (int k = 0; k < i2; ++k) s = fmaf(__shfl_sync(full, d[k], i2), x[k], s);
+      const float lii = __shfl_sync(full, d[i2], i2);
+      x[i2] = ((i2 == l ? 1.f : 0.f) - s) / lii;
+    }
+    if (lane < SB) {
+#pragma unroll
+      for (int c = 0; c < SB; ++c) Xs.a[o + c][o + l] = x[c];
+    }
+  }
+  __syncthreads();
+  for (int b = SB; b < NB; b *= 2) {   // inv([[A,0],[C,D]]) = [[Ai,0],[-Di C Ai, Di]]
+    const int npairs = NB / (2 * b), bb = b * b, sh = (b == SB) ? 4 : 5;
+    for (int e = tid; e < npairs * bb; e += kPotfThreads) {
+      const int pr = e / bb, rem = e - pr * bb, r = rem >> sh, c = rem & (b - 1), p0 = pr * 2 * b;
+      float s = 0.f;
+      for (int k = c; k < b; ++k) s = fmaf(As.a[p0 + b + r][p0 + k], Xs.a[p0 + k][p0 + c], s);
       Ts[pr * b + r][c] = s;
     }
     __syncthreads();
-    // X = -Di . T,  Di = Xs[p + b .., p + b ..] lower triangular
-    for (int e = tid; e < npairs * b * b; e += kPotfThreads) {
-      const int pr = e / (b * b), rem = e - pr * b * b, r = rem / b, c = rem - r * b, p0 = pr * 2 * b;
+    for (int e = tid; e < npairs * bb; e += kPotfThreads) {
+      const int pr = e / bb, rem = e - pr * bb, r = rem >> sh, c = rem & (b - 1), p0 = pr * 2 * b;
       float s = 0.f;
-      for (int k = 0; k <= r; ++k) s = fmaf(Xs[p0 + b + r][p0 + b + k], Ts[pr * b + k][c], s);
-      Xs[p0 + b + r][p0 + c] = -s;
+      for (int k = 0; k <= r; ++k) s = fmaf(Xs.a[p0 + b + r][p0 + b + k], Ts[pr * b + k][c], s);
+      Xs.a[p0 + b + r][p0 + c] = -s;
     }
     __syncthreads();
   }
+}
 
+// Panel step of the blocked Cholesky.  D: the 64 x 64 diagonal block (read only here), Ld: where L11 goes,
+// P: the rows below it (ld = lda), overwritten with L21.  Grid = 1 + ceil(rows_below / 64).
+__global__ void __launch_bounds__(kPotfThreads) chol_panel_kernel(const float* __restrict__ D, float* __restrict__ P,
+                                                                  int64_t lda, int rows_below,
+                                                                  float* __restrict__ Ld) {
+  __shared__ Block64 As;
+  __shared__ Block64 Xs;
+  __shared__ float rd16[SB];
+  __shared__ float li16[NB / SB][SB][SB + 1];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += kPotfThreads) As.a[e >> 6][e & 63] = D[(int64_t)(e >> 6) * lda + (e & 63)];
+  for (int e = tid; e < (NB / SB) * SB * (SB + 1); e += kPotfThreads) (&li16[0][0][0])[e] = 0.f;
+  const int row0 = ((int)blockIdx.x - 1) * NB;
+  if (blockIdx.x > 0) {
+    for (int e = tid; e < NB * NB; e += kPotfThreads) {
+      const int r = e >> 6, c = e & 63;
+      Xs.a[r][c] = (row0 + r < rows_below) ? P[(int64_t)(row0 + r) * lda + c] : 0.f;
+    }
+  }
+  __syncthreads();
+  factor64(As, rd16, li16);
+  if (blockIdx.x == 0) {
+    for (int e = tid; e < NB * NB; e += kPotfThreads) Ld[e] = As.a[e >> 6][e & 63];
+    return;
+  }
+  __syncthreads();
+  {  // X L11^T = A21, 16 columns at a time: T = A_cb - sum_{kb<cb} X_kb L[cb][kb]^T ; X_cb = T Li_cb^T.
+     // thread = (row r, 4 adjacent columns); the 4 threads of a row sit in one warp, so __syncwarp is enough.
+    const int r = tid >> 2, cq = (tid & 3) * 4;
+    for (int cb = 0; cb < NB / SB; ++cb) {
+      const int o = cb * SB;
+      float t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = Xs.a[r][o + cq + j];
+      for (int k = 0; k < o; ++k) {
+        const float xk = Xs.a[r][k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = fmaf(-xk, As.a[o + cq + j][k], t[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Xs.a[r][o + cq + j] = t[j];
+      __syncwarp();
+      float tr[SB];
+#pragma unroll
+      for (int k = 0; k < SB; ++k) tr[k] = Xs.a[r][o + k];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float sx = 0.f;
+#pragma unroll
+        for (int k = 0; k < SB; ++k) sx = fmaf(tr[k], li16[cb][cq + j][k], sx);   // Li is lower: entries k > c are 0
+        Xs.a[r][o + cq + j] = sx;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
   for (int e = tid; e < NB * NB; e += kPotfThreads) {
     const int r = e >> 6, c = e & 63;
-    A[(int64_t)r * lda + c] = (c <= r) ? As[r][c] : 0.f;
-    Dinv[(int64_t)r * ldd + c] = Xs[r][c];
+    if (row0 + r < rows_below) P[(int64_t)(row0 + r) * lda + c] = Xs.a[r][c];
   }
+}
+
+// Linv diagonal blocks: one CTA per 64 x 64 diagonal factor (Ld[j]) -> Linv[j*64.., j*64..] (ld = ldd).
+__global__ void __launch_bounds__(kPotfThreads) diag_inv_kernel(const float* __restrict__ Ld, float* __restrict__ Linv,
+                                                                int64_t ldd) {
+  __shared__ Block64 As;
+  __shared__ Block64 Xs;
+  __shared__ float Ts[NB / 2][NB / 2 + 1];
+  const int tid = threadIdx.x;
+  const float* src = Ld + (size_t)blockIdx.x * NB * NB;
+  for (int e = tid; e < NB * NB; e += kPotfThreads) As.a[e >> 6][e & 63] = src[e];
+  __syncthreads();
+  invert64(As, Xs, Ts);
+  float* dst = Linv + (int64_t)blockIdx.x * NB * (ldd + 1);
+  for (int e = tid; e < NB * NB; e += kPotfThreads) dst[(int64_t)(e >> 6) * ldd + (e & 63)] = Xs.a[e >> 6][e & 63];
+}
+
+// Copy the diagonal factors back into the big matrix (so Bm holds the complete Lc).
+__global__ void __launch_bounds__(kPotfThreads) diag_store_kernel(const float* __restrict__ Ld, float* __restrict__ Bm,
+                                                                  int64_t ld) {
+  const float* src = Ld + (size_t)blockIdx.x * NB * NB;
+  float* dst = Bm + (int64_t)blockIdx.x * NB * (ld + 1);
+  for (int e = threadIdx.x; e < NB * NB; e += kPotfThreads) dst[(int64_t)(e >> 6) * ld + (e & 63)] = src[e];
 }
 
 // ------------------------------------------------------------------ reductions
@@ -254,7 +370,7 @@ int launch_vbs(const double* scal, int64_t n_total, int Q, int L, float* vbs, cu
 // same factorisation twice per epoch, at :235 and inside :166; the caller caches this buffer).
 struct FactorLayout {
   int Qp;
-  size_t off_bm, off_linv, off_tm, off_part, off_tn, total;
+  size_t off_bm, off_linv, off_tm, off_ld, off_part, off_tn, total;
   size_t tn_bytes;
 };
 
@@ -266,6 +382,7 @@ static FactorLayout factor_layout(int Q) {
   f.off_bm = o;   o += qq;
   f.off_linv = o; o += qq;
   f.off_tm = o;   o += qq;
+  f.off_ld = o;   o += align_up((size_t)f.Qp * NB * sizeof(float), 256);   // the 64 x 64 diagonal factors
   f.off_part = o; o += align_up((size_t)kSumsqBlocks * sizeof(double), 256);
   f.off_tn = o;
   f.tn_bytes = tn_workspace_bytes(Q, Q, Q, 0, 1);
@@ -320,26 +437,28 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
   }
   GPP_CUDA(cudaMemsetAsync(Linv, 0, (size_t)Qp * Qp * sizeof(float), st));
 
-  // ---- blocked right-looking Cholesky
+  // ---- blocked right-looking Cholesky: per 64-wide panel ONE fused kernel (diagonal factor + panel solve) and one
+  //      trailing update; the diagonal factors are parked in Ld so that no CTA reads a block another one rewrites
+  float* Ld = reinterpret_cast<float*>(base + f.off_ld);
   for (int j = 0; j < nb; ++j) {
     const int k0 = j * NB;
-    float* diag = Bm + (int64_t)k0 * (Qp + 1);
-    float* dinv = Linv + (int64_t)k0 * (Qp + 1);
-    potf2_inv_kernel<<<1, kPotfThreads, 0, st>>>(diag, Qp, dinv, Qp);
-    GPP_LAUNCH_CHECK();
     const int rem = Qp - k0 - NB;
-    if (rem <= 0) break;
+    const float* diag = Bm + (int64_t)k0 * (Qp + 1);
     float* panel = Bm + (int64_t)(k0 + NB) * Qp + k0;  // A21, becomes L21 in place
-    GemmParams p{};
-    p.A = panel; p.lda = Qp; p.B = dinv; p.ldb = Qp; p.C = panel; p.ldc = Qp;
-    p.M = rem; p.N = NB; p.K = NB; p.M_last = -1; p.alpha = 1.f; p.beta = 0.f;
-    GPP_TRY(launch_gemm(p, false, false, 1, st));  // L21 = A21 . Dinv^T
+    chol_panel_kernel<<<1 + (rem > 0 ? (rem + NB - 1) / NB : 0), kPotfThreads, 0, st>>>(diag, panel, Qp, rem,
+                                                                                         Ld + (size_t)j * NB * NB);
+    GPP_LAUNCH_CHECK();
+    if (rem <= 0) break;
     GemmParams s{};
     s.A = panel; s.lda = Qp; s.B = panel; s.ldb = Qp;
     s.C = Bm + (int64_t)(k0 + NB) * (Qp + 1); s.ldc = Qp;
     s.M = rem; s.N = rem; s.K = NB; s.M_last = -1; s.alpha = -1.f; s.beta = 1.f; s.lower_only = 1;
     GPP_TRY(launch_gemm(s, false, false, 1, st));  // A22 -= L21 . L21^T (lower tiles)
   }
+  diag_store_kernel<<<nb, kPotfThreads, 0, st>>>(Ld, Bm, Qp);
+  GPP_LAUNCH_CHECK();
+  diag_inv_kernel<<<nb, kPotfThreads, 0, st>>>(Ld, Linv, Qp);
+  GPP_LAUNCH_CHECK();
 
   // ---- Linv by recursive doubling: inv([[A,0],[C,D]]) = [[Ai,0],[-Di C Ai, Di]]
   for (int b = NB; b < Qp; b *= 2) {
