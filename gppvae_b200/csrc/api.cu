@@ -62,7 +62,7 @@ extern "C" int gpp_gram_vtz(const float* V, int64_t ldv, const float* X, int64_t
   GPP_REQUIRE(mat_ok(V, ldv, Q), "gram_vtz: V must be 16-byte aligned with ldv >= Q and ldv %% 4 == 0");
   GPP_REQUIRE(L == 0 || mat_ok(X, ldx, L), "gram_vtz: X must be 16-byte aligned with ldx >= L and ldx %% 4 == 0");
   GPP_REQUIRE(mat_ok(GC, ldgc, (int64_t)Q + L), "gram_vtz: GC must be 16-byte aligned with ldgc >= Q + L");
-  // large problems run on the tensor cores (3xTF32); tiles that cannot fill a 128 x 256 UMMA use the fp32 tile engine
+  // large problems run on the tensor cores (3xTF32); tiles that cannot fill a 256 x 256 pair UMMA use the fp32 tile engine
   if (tc_pass1_supported(n, Q, L))
     return launch_tc_pass1(V, ldv, X, ldx, n, Q, L, GC, ldgc, workspace, workspace_bytes, (cudaStream_t)stream);
   return launch_tn(V, ldv, Q, V, ldv, Q, X, ldx, L, n, 1, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes,

@@ -1,25 +1,36 @@
-// Pass 1 on the 5th-generation tensor cores:  GC = V^T [V | X]  as 3xTF32 (hi.hi + hi.lo + lo.hi).
+// Pass 1, pass 2 and Vb on the 5th-generation tensor cores as 3xTF32 (hi.hi + hi.lo + lo.hi), on CTA PAIRS.
 //
-//   D(128 x 256 tile) = sum_k A[k, m]^T B[k, n]      A = V[:, 128 tm ..], B = V[:, 256 tn ..] or X[:, 256 j ..]
+// Every GEMM tile is 256 x 256 and belongs to a cluster of two CTAs (tcgen05 cta_group::2): each CTA stages ITS 128
+// rows of the M operand and ITS 128 columns of the N operand, the leader CTA issues M = 256, N = 256, K = 8 MMAs that
+// read both CTAs' shared memory, and each CTA's TMEM receives its 128 accumulator rows.  Per MMA a CTA's shared
+// memory serves 4 KB (A) + 4 KB (its half of B) instead of the 4 + 8 KB of a 1-CTA 128 x 256 MMA, and per k-row the
+// TMA / converter traffic drops by a third -- the 1-CTA version of this kernel was shared-memory-bandwidth bound
+// (MMA operand reads 96 B/clk + converter 64 B/clk + TMA 32 B/clk against 128 B/clk per SM; measured 69 % of the
+// tensor pipe); the pair version needs 64 + 43 + 21 B/clk.
 //
-// Both operands are row-major with the contraction running over ROWS, i.e. MN-major UMMA operands.  For tf32 the
-// only MN-major shared-memory layout is SWIZZLE_128B_BASE32B (atom = 32 floats x 4 k-rows, 32-byte chunks XORed
-// with row % 4), which is exactly what a TMA box of {32 floats, BK rows} with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-// writes: LBO = BK * 128 B between 32-float column groups, SBO = 512 B between 4-row k-groups, 1024 B per K = 8 step.
+//   pass 1:  D = sum_k A[k, m]^T B[k, n]   A = V[:, 256 tm ..], B = V[:, 256 tn ..] or X[:, 256 j ..]
+//            both operands row-major with the contraction over ROWS = MN-major UMMA operands; for tf32 the only
+//            MN-major layout is SWIZZLE_128B_BASE32B (atom = 32 floats x 4 k-rows, 32-byte chunks XORed with
+//            row % 4), which is what a TMA box {32 floats, BK rows} with SWIZZLE_128B_ATOM_32B writes:
+//            LBO = BK * 128 B between 32-float column groups, SBO = 512 B between 4-row k-groups, 1 KB per K = 8.
+//   rows  :  D = sum_k [A1 | A2][row, k] B[k, col]   (pass 2: A1 = V, B = W; Vb: A1 = V, A2 = Xb, B = [rL Binv; -W^T])
+//            A is K-major: TMA box {16 floats, 128 rows} with SWIZZLE_64B, SBO = 512 B, +32 B per K = 8 step.
 //
-// Measured on B200 (experiments/tc/exp1_gram.cu): kind::tf32 TRUNCATES fp32 operands to tf32 and the TMEM
-// accumulator is rounded toward zero after every MMA (relative bias ~1.5e-8 per accumulation).  Hence
-//   * the raw fp32 tile is the hi operand as it stands (the hardware truncation IS the split) and the converter
-//     warps only write lo = rn_tf32(a - trunc_tf32(a)); measured against the variant that rounds hi to nearest and
-//     stores it back: same error (5-7e-7 of max|G|, no measurable bias) and 10 % faster (less shared-memory traffic,
-//     which is what bounds this kernel);
-//   * accumulation in TMEM is limited to WINDOWS of kWinStages stages (24 MMAs, bias <= 3.6e-7 of the window sum);
-//     windows ping-pong between two TMEM buffers and are summed in fp32 registers (round-to-nearest) by the drain
-//     warps, which keeps G and C at fp32-level accuracy for any N.
+// Numerics (measured on B200, experiments/tc/exp1_gram.cu): kind::tf32 TRUNCATES fp32 operands and the TMEM
+// accumulator is rounded toward zero after every MMA.  Hence
+//   * the raw fp32 tile is the hi operand as it stands (the hardware truncation is the split); the converter warps
+//     only write lo = rn_tf32(a - trunc_tf32(a));
+//   * accumulation in TMEM is limited to WINDOWS of kWin stages; inside a window the small cross terms (hi.lo, lo.hi)
+//     of ALL its stages are issued first, while the accumulator is still tiny (their truncation error is negligible
+//     there), and the hi.hi terms last, so only 2 kWin truncations per window happen at full magnitude;
+//   * windows ping-pong between two TMEM buffers and are summed in fp32 registers (round-to-nearest) by the drain warps.
 //
-// Warp roles (512 threads, 4 warpgroups, setmaxnreg re-balanced): warp 0 TMA producer, warp 1 MMA issuer + TMEM
-// owner, warps 4-7 converters, warps 8-15 drain.  Persistent over (tile, k-split) units; deterministic split-K:
-// every unit writes its own partial tile, tc_reduce_kernel sums them in a fixed order (fp64) and mirrors G.
+// Warp roles per CTA (512 threads, setmaxnreg re-balanced): warp 0 TMA producer (own halves), warp 1 MMA issuer
+// (leader CTA only) + TMEM owner, warps 4-7 converters, warps 8-15 drain / epilogue of the CTA's own 128 rows.
+// Barriers: full[s] (local TMA -> local converters), conv[s] (converters of BOTH CTAs -> leader), empty[s] and
+// tfull[b] (MMA commit, multicast to both CTAs), tempty[b] (drain warps of both CTAs -> leader).
+// Pass 1 is persistent over (tile, k-split) units with a deterministic split-K: every unit writes its own partial
+// tile, tc_reduce_kernel sums them in a fixed order (fp64) and tc_mirror_kernel fills the upper triangle of G.
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -33,14 +44,34 @@ namespace {
 #ifndef GPP_TC_WIN
 #define GPP_TC_WIN 4
 #endif
-#ifndef GPP_TC_STORE_HI
-#define GPP_TC_STORE_HI 0   // 0: raw fp32 is the hi operand (kind::tf32 truncates it in hardware); 1: hi = rn_tf32(a) written back
+#ifndef GPP_TC_STAGES
+#define GPP_TC_STAGES 6
 #endif
-constexpr int TM = 128, TN = 256, TBK = 16, kStages = 4, kWinStages = GPP_TC_WIN;
-constexpr int kABytes = TM * TBK * 4, kBBytes = TN * TBK * 4, kRawBytes = kABytes + kBBytes;  // 8 K + 16 K
-constexpr int kStageBytes = 2 * kRawBytes;                                                     // raw(hi) + lo
+constexpr int TM = 256, TN = 256;   // tile of a CTA pair
+constexpr int HM = 128, HN = 128;   // what one CTA stages of it
+#ifndef GPP_TC_GROUP
+#define GPP_TC_GROUP 2
+#endif
+constexpr int TBK = 16, kStages = GPP_TC_STAGES, kWin = GPP_TC_WIN, kGroup = GPP_TC_GROUP;
+constexpr int kABytes = HM * TBK * 4, kBBytes = HN * TBK * 4, kRawBytes = kABytes + kBBytes;   // 8 K + 8 K
+constexpr int kStageBytes = 2 * kRawBytes;                                                      // raw (= hi) + lo
 constexpr int kTcThreads = 512;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(kGroup >= 1 && kGroup <= kWin && kGroup < kStages, "a group must fit in the stage ring with room to prefetch");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+// Optional role profiling (-DGPP_TC_PROF): cycles each role spends waiting on its barriers, per CTA.
+#ifdef GPP_TC_PROF
+__device__ unsigned long long g_prof[512][16];
+#define PROF_DECL unsigned long long pw0 = 0, pw1 = 0; const unsigned long long pt0 = clock64()
+#define PROF_WAIT(var, stmt) do { const unsigned long long c0__ = clock64(); stmt; var += clock64() - c0__; } while (0)
+#define PROF_STORE(slot) do { g_prof[blockIdx.x][(slot) * 3 + 0] = pw0; g_prof[blockIdx.x][(slot) * 3 + 1] = pw1; \
+                              g_prof[blockIdx.x][(slot) * 3 + 2] = clock64() - pt0; } while (0)
+#else
+#define PROF_DECL unsigned long long pw0 = 0, pw1 = 0
+#define PROF_WAIT(var, stmt) stmt
+#define PROF_STORE(slot) do { } while (0)
+#endif
 
 struct TcShared {
   uint64_t full[kStages], conv[kStages], empty[kStages], tfull[2], tempty[2];
@@ -50,8 +81,8 @@ struct TcShared {
 struct Pass1Params {
   int64_t n;
   int Q, L;
-  int tm_count;      // ceil(Q / 128)
-  int tiles_g;       // tiles of G: (tm, tn) with tn <= tm / 2
+  int tm_count;      // ceil(Q / 256)
+  int tiles_g;       // lower-triangular tiles of G: (tm, tn) with tn <= tm
   int tn_c;          // ceil(L / 256)
   int tiles;         // tiles_g + tm_count * tn_c
   int splits;
@@ -62,13 +93,10 @@ struct Pass1Params {
 __device__ __forceinline__ void decode_tile(const Pass1Params& p, int tile, int& tm, int& tn, bool& is_c) {
   if (tile < p.tiles_g) {
     is_c = false;
-    int t = 0, acc = 0;
-    while (acc + (t >> 1) + 1 <= tile) {
-      acc += (t >> 1) + 1;
-      ++t;
-    }
+    int t = 0;
+    while ((t + 1) * (t + 2) / 2 <= tile) ++t;
     tm = t;
-    tn = tile - acc;
+    tn = tile - t * (t + 1) / 2;
   } else {
     is_c = true;
     const int r = tile - p.tiles_g;
@@ -82,152 +110,210 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
-tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmX, Pass1Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+// ---- pieces shared by the two kernels ----------------------------------------------------------------------
+__device__ __forceinline__ TcShared* tc_prologue(uint8_t* base, uint32_t& tmem) {
   TcShared* sm = reinterpret_cast<TcShared*>(base + kStages * kStageBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm->full[s], 1);
-      mbar_init(&sm->conv[s], 4);
+      mbar_init(&sm->conv[s], 8);     // 4 converter warps x 2 CTAs (used in the leader)
       mbar_init(&sm->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm->tfull[b], 1);
-      mbar_init(&sm->tempty[b], 8);
+      mbar_init(&sm->tempty[b], 16);  // 8 drain warps x 2 CTAs (used in the leader)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&sm->tmem_base, 512);
+  if ((threadIdx.x >> 5) == 1) tmem_alloc_pair(&sm->tmem_base, 512);
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated
   tcgen05_fence_after();
-  const uint32_t tmem = sm->tmem_base;
+  tmem = sm->tmem_base;
+  return sm;
+}
+
+__device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
+  tcgen05_fence_before();
+  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still touch its shared memory / barriers
+  if ((threadIdx.x >> 5) == 1) tmem_dealloc_pair(tmem, 512);
+}
+
+// converter warps: wait for the raw tile of stage s, write the lo plane, tell the leader
+__device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint32_t conv0_leader, uint32_t it,
+                                              unsigned long long& pw0) {
+  const int t = threadIdx.x - 128, lane = threadIdx.x & 31;
+  const int s = it % kStages;
+  PROF_WAIT(pw0, mbar_wait(&sm->full[s], (it / kStages) & 1));
+  const float4* raw = reinterpret_cast<const float4*>(base + s * kStageBytes);
+  float4* lo = reinterpret_cast<float4*>(base + s * kStageBytes + kRawBytes);
+#pragma unroll
+  for (int i = 0; i < kRawBytes / 16 / 128; ++i) {
+    const float4 v = raw[t + i * 128];
+    float4 l;
+    l.x = tf32_rn(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+    l.y = tf32_rn(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+    l.z = tf32_rn(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+    l.w = tf32_rn(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+    lo[t + i * 128] = l;
+  }
+  fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(conv0_leader + 8u * s);
+}
+
+// MMA issuer (one thread of the leader): one window of `wst` stages starting at ring position `it` into TMEM buffer d.
+// The window is issued in GROUPS of kGroup stages: wait for the group's stages, issue the cross terms (hi.lo, lo.hi)
+// of the whole group, then its hi.hi terms, releasing each stage's slot right after its hi.hi MMAs.
+// A_MN: A operand MN-major (pass 1) or K-major (rows kernel).
+template <bool A_MN>
+__device__ __forceinline__ void issue_window(uint8_t* base, TcShared* sm, uint32_t d, uint32_t it, int wst,
+                                             unsigned long long& pw1) {
+  constexpr uint32_t idesc = umma_idesc_tf32(TM, TN, A_MN, true);
+  uint32_t acc = 0;
+  for (int g0 = 0; g0 < wst; g0 += kGroup) {
+    const int g1 = min(wst, g0 + kGroup);
+    PROF_WAIT(pw1, for (int j = g0; j < g1; ++j)
+                       mbar_wait_cluster(&sm->conv[(it + j) % kStages], ((it + j) / kStages) & 1));
+    tcgen05_fence_after();
+    for (int j = g0; j < g1; ++j) {
+      const uint32_t a_hi = smem_u32(base + ((it + j) % kStages) * kStageBytes), b_hi = a_hi + kABytes;
+      const uint32_t a_lo = a_hi + kRawBytes, b_lo = a_lo + kABytes;
+#pragma unroll
+      for (int kk = 0; kk < TBK / 8; ++kk) {
+        const uint64_t dah = A_MN ? umma_desc(a_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32)
+                                  : umma_desc(a_hi + kk * 32, 16, 512, kLayoutSw64);
+        const uint64_t dal = A_MN ? umma_desc(a_lo + kk * 1024, TBK * 128, 512, kLayoutSw128Base32)
+                                  : umma_desc(a_lo + kk * 32, 16, 512, kLayoutSw64);
+        const uint64_t dbh = umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
+        const uint64_t dbl = umma_desc(b_lo + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
+        umma_tf32_pair(d, dah, dbl, idesc, acc);
+        umma_tf32_pair(d, dal, dbh, idesc, 1);
+        acc = 1;
+      }
+    }
+    for (int j = g0; j < g1; ++j) {
+      const int s = (it + j) % kStages;
+      const uint32_t a_hi = smem_u32(base + s * kStageBytes), b_hi = a_hi + kABytes;
+#pragma unroll
+      for (int kk = 0; kk < TBK / 8; ++kk) {
+        const uint64_t dah = A_MN ? umma_desc(a_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32)
+                                  : umma_desc(a_hi + kk * 32, 16, 512, kLayoutSw64);
+        const uint64_t dbh = umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
+        umma_tf32_pair(d, dah, dbh, idesc, 1);
+      }
+      umma_commit_pair(&sm->empty[s], 3);
+    }
+  }
+}
+
+// drain warps: add one finished window (this CTA's 128 rows x this warp's 128 columns) into registers
+__device__ __forceinline__ void drain_window(TcShared* sm, uint32_t tmem, uint32_t tempty0_leader, uint32_t wc,
+                                             float (&acc)[128], unsigned long long& pw0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const int half = (warp - 8) >> 2;
+  const uint32_t buf = wc & 1;
+  PROF_WAIT(pw0, mbar_wait(&sm->tfull[buf], (wc >> 1) & 1));
+  tcgen05_fence_after();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float v[32];
+    tmem_ld_32x32(tmem + lane_addr + buf * TN + half * 128 + c * 32, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
+  }
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(tempty0_leader + 8u * buf);
+}
+
+// =====================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmX, Pass1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  uint32_t tmem;
+  TcShared* sm = tc_prologue(base, tmem);
   const int nunits = p.tiles * p.splits;
 
   if (warp < 4) {
     setmaxnreg_dec<40>();
-    if (warp == 0) {
-      // ===================================================== TMA producer
-      if (lane == 0) {
-        tma_prefetch_desc(&tmV);
-        tma_prefetch_desc(&tmX);
-        uint32_t it = 0;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-          const int split = u / p.tiles, tile = u - split * p.tiles;  // consecutive CTAs share a k-range (L2 reuse)
-          int tm, tn;
-          bool is_c;
-          decode_tile(p, tile, tm, tn, is_c);
-          const int64_t r0 = (int64_t)split * p.rows_per_split;
-          const int64_t r1 = min(p.n, r0 + p.rows_per_split);
-          const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
-          const CUtensorMap* mb = is_c ? &tmX : &tmV;
-          for (int st = 0; st < nst; ++st, ++it) {
-            const int s = it % kStages;
-            mbar_wait(&sm->empty[s], ((it / kStages) & 1) ^ 1);
-            uint8_t* dst = base + s * kStageBytes;
-            const int row = (int)(r0 + (int64_t)st * TBK);
-            mbar_arrive_expect_tx(&sm->full[s], kRawBytes);
-#pragma unroll
-            for (int g = 0; g < TM / 32; ++g) tma_load_2d(dst + g * (TBK * 128), &tmV, tm * TM + g * 32, row, &sm->full[s]);
-#pragma unroll
-            for (int g = 0; g < TN / 32; ++g)
-              tma_load_2d(dst + kABytes + g * (TBK * 128), mb, tn * TN + g * 32, row, &sm->full[s]);
-          }
-        }
-      }
-    } else if (warp == 1) {
-      // ===================================================== MMA issuer
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_tf32(TM, TN, true, true);
-        uint32_t it = 0, wc = 0;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-          const int split = u / p.tiles;
-          const int64_t r0 = (int64_t)split * p.rows_per_split;
-          const int64_t r1 = min(p.n, r0 + p.rows_per_split);
-          const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
-          for (int st0 = 0; st0 < nst; st0 += kWinStages, ++wc) {
-            const uint32_t buf = wc & 1;
-            mbar_wait(&sm->tempty[buf], ((wc >> 1) & 1) ^ 1);
-            tcgen05_fence_after();
-            const uint32_t d = tmem + buf * TN;
-            const int wst = min(kWinStages, nst - st0);
-            for (int j = 0; j < wst; ++j, ++it) {
-              const int s = it % kStages;
-              mbar_wait(&sm->conv[s], (it / kStages) & 1);
-              tcgen05_fence_after();
-              const uint32_t a_hi = smem_u32(base + s * kStageBytes), b_hi = a_hi + kABytes;
-              const uint32_t a_lo = a_hi + kRawBytes, b_lo = a_lo + kABytes;
-#pragma unroll
-              for (int kk = 0; kk < TBK / 8; ++kk) {
-                const uint32_t o = kk * 1024;
-                const uint64_t dah = umma_desc(a_hi + o, TBK * 128, 512, kLayoutSw128Base32);
-                const uint64_t dbh = umma_desc(b_hi + o, TBK * 128, 512, kLayoutSw128Base32);
-                const uint64_t dal = umma_desc(a_lo + o, TBK * 128, 512, kLayoutSw128Base32);
-                const uint64_t dbl = umma_desc(b_lo + o, TBK * 128, 512, kLayoutSw128Base32);
-                umma_tf32(d, dah, dbh, idesc, (j | kk) != 0);
-                umma_tf32(d, dah, dbl, idesc, 1);
-                umma_tf32(d, dal, dbh, idesc, 1);
-              }
-              umma_commit(&sm->empty[s]);   // smem slot free once these MMAs have read it
-            }
-            umma_commit(&sm->tfull[buf]);   // window complete
-          }
-        }
-      }
-    }
-  } else if (warp < 8) {
-    setmaxnreg_dec<96>();
-    {
-      // ===================================================== converters: fp32 -> (hi, lo) tf32 planes
-      const int t = threadIdx.x - 128;  // 0..127
+    if (warp == 0 && lane == 0) {
+      // ===================================================== TMA producer (this CTA's halves of A and B)
+      PROF_DECL;
+      tma_prefetch_desc(&tmV);
+      tma_prefetch_desc(&tmX);
       uint32_t it = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      for (int u = pair; u < nunits; u += npairs) {
+        const int split = u / p.tiles, tile = u - split * p.tiles;   // consecutive pairs share a k-range (L2 reuse)
+        int tm, tn;
+        bool is_c;
+        decode_tile(p, tile, tm, tn, is_c);
+        const int64_t r0 = (int64_t)split * p.rows_per_split;
+        const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+        const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
+        const CUtensorMap* mb = is_c ? &tmX : &tmV;
+        const int acol = tm * TM + (int)rank * HM, bcol = tn * TN + (int)rank * HN;
+        for (int st = 0; st < nst; ++st, ++it) {
+          const int s = it % kStages;
+          PROF_WAIT(pw0, mbar_wait(&sm->empty[s], ((it / kStages) & 1) ^ 1));
+          uint8_t* dst = base + s * kStageBytes;
+          const int row = (int)(r0 + (int64_t)st * TBK);
+          mbar_arrive_expect_tx(&sm->full[s], kRawBytes);
+#pragma unroll
+          for (int g = 0; g < HM / 32; ++g) tma_load_2d(dst + g * (TBK * 128), &tmV, acol + g * 32, row, &sm->full[s]);
+#pragma unroll
+          for (int g = 0; g < HN / 32; ++g)
+            tma_load_2d(dst + kABytes + g * (TBK * 128), mb, bcol + g * 32, row, &sm->full[s]);
+        }
+      }
+      PROF_STORE(0);
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      // ===================================================== MMA issuer (leader CTA)
+      PROF_DECL;
+      uint32_t it = 0, wc = 0;
+      for (int u = pair; u < nunits; u += npairs) {
         const int split = u / p.tiles;
         const int64_t r0 = (int64_t)split * p.rows_per_split;
         const int64_t r1 = min(p.n, r0 + p.rows_per_split);
         const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
-        for (int st = 0; st < nst; ++st, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&sm->full[s], (it / kStages) & 1);
-          float4* raw = reinterpret_cast<float4*>(base + s * kStageBytes);
-          float4* lo = reinterpret_cast<float4*>(base + s * kStageBytes + kRawBytes);
-#pragma unroll 4
-          for (int i = t; i < kRawBytes / 16; i += 128) {
-            const float4 v = raw[i];
-            float4 l;
-#if GPP_TC_STORE_HI
-            float4 h;
-            split_tf32(v.x, h.x, l.x);
-            split_tf32(v.y, h.y, l.y);
-            split_tf32(v.z, h.z, l.z);
-            split_tf32(v.w, h.w, l.w);
-            raw[i] = h;
-#else
-            l.x = tf32_rn(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
-            l.y = tf32_rn(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
-            l.z = tf32_rn(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
-            l.w = tf32_rn(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-#endif
-            lo[i] = l;
-          }
-          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm->conv[s]);
+        for (int st0 = 0; st0 < nst; st0 += kWin, ++wc) {
+          const uint32_t buf = wc & 1;
+          PROF_WAIT(pw0, mbar_wait_cluster(&sm->tempty[buf], ((wc >> 1) & 1) ^ 1));
+          const int wst = min(kWin, nst - st0);
+          issue_window<true>(base, sm, tmem + buf * TN, it, wst, pw1);
+          umma_commit_pair(&sm->tfull[buf], 3);   // window complete in both CTAs' TMEM
+          it += wst;
         }
       }
+      PROF_STORE(1);
     }
+  } else if (warp < 8) {
+    setmaxnreg_dec<96>();
+    // ======================================================= converters
+    PROF_DECL;
+    const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
+    uint32_t it = 0;
+    for (int u = pair; u < nunits; u += npairs) {
+      const int split = u / p.tiles;
+      const int64_t r0 = (int64_t)split * p.rows_per_split;
+      const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+      const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
+      for (int st = 0; st < nst; ++st, ++it) convert_stage(base, sm, conv0, it, pw0);
+    }
+    if (threadIdx.x == 128) PROF_STORE(2);
   } else {
     // ======================================================= drain warps: TMEM windows -> fp32 registers -> partial tile
     setmaxnreg_inc<184>();
-    const int q = warp & 3;               // TMEM lane quadrant this warp may touch
-    const int half = (warp - 8) >> 2;     // columns [128 half, 128 half + 128)
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    PROF_DECL;
+    const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
+    const int q = warp & 3, half = (warp - 8) >> 2;
     uint32_t wc = 0;
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+    for (int u = pair; u < nunits; u += npairs) {
       const int split = u / p.tiles, tile = u - split * p.tiles;
       const int64_t r0 = (int64_t)split * p.rows_per_split;
       const int64_t r1 = min(p.n, r0 + p.rows_per_split);
@@ -235,43 +321,29 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-      for (int st0 = 0; st0 < nst; st0 += kWinStages, ++wc) {
-        const uint32_t buf = wc & 1;
-        mbar_wait(&sm->tfull[buf], (wc >> 1) & 1);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tmem_ld_32x32(tmem + lane_addr + buf * TN + half * 128 + c * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm->tempty[buf]);
-      }
-      float* out = p.partial + ((size_t)tile * p.splits + split) * (size_t)(TM * TN) + (size_t)(q * 32 + lane) * TN +
-                   half * 128;
+      for (int st0 = 0; st0 < nst; st0 += kWin, ++wc) drain_window(sm, tmem, tempty0, wc, acc, pw0);
+      float* out = p.partial + ((size_t)tile * p.splits + split) * (size_t)(TM * TN) +
+                   (size_t)(rank * HM + q * 32 + lane) * TN + half * 128;
 #pragma unroll
       for (int i = 0; i < 128; i += 4)
         *reinterpret_cast<float4*>(out + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
     }
+    if (threadIdx.x == 256) PROF_STORE(3);
   }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  tc_epilogue(tmem);
 }
 
 // GC[r][c] = sum_s partial[tile][s][..] for every computed tile (fixed order, fp64 accumulation).
+// grid = tiles * 8: CTA (tile, j) reduces rows [32 j, 32 j + 32) of the tile.
 __global__ void __launch_bounds__(256) tc_reduce_kernel(Pass1Params p, float* __restrict__ GC, int64_t ldgc) {
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x >> 3, rblk = blockIdx.x & 7;
   int tm, tn;
   bool is_c;
   decode_tile(p, tile, tm, tn, is_c);
   const int ncols = is_c ? p.L : p.Q;
-  const int col0 = tn * TN, row0 = tm * TM;
-  const float* src = p.partial + (size_t)tile * p.splits * (size_t)(TM * TN);
-  for (int e = threadIdx.x; e < TM * TN / 4; e += blockDim.x) {
+  const int col0 = tn * TN, row0 = tm * TM + rblk * 32;
+  const float* src = p.partial + (size_t)tile * p.splits * (size_t)(TM * TN) + (size_t)rblk * 32 * TN;
+  for (int e = threadIdx.x; e < 32 * TN / 4; e += blockDim.x) {
     const int r = e / (TN / 4), c4 = (e - r * (TN / 4)) * 4;
     if (row0 + r >= p.Q || col0 + c4 >= ncols) continue;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -290,7 +362,6 @@ __global__ void __launch_bounds__(256) tc_mirror_kernel(float* __restrict__ G, i
   const int bx = blockIdx.x, by = blockIdx.y;   // block (by, bx) of 32 x 32, processed only when bx >= by
   if (bx < by) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  // read lower block (rows 32 bx.., cols 32 by..)
   for (int i = ty; i < 32; i += 8) {
     const int r = bx * 32 + i, c = by * 32 + tx;
     tile[i][tx] = (r < Q && c < Q) ? G[(int64_t)r * ldg + c] : 0.f;
@@ -303,20 +374,17 @@ __global__ void __launch_bounds__(256) tc_mirror_kernel(float* __restrict__ G, i
 }
 
 // =====================================================================================================
-// Row GEMM on tcgen05:  D(128 rows x 256 cols) = sum_k [A1 | A2][row, k] * B[k, col]     (3xTF32, windowed)
+// Row GEMM:  D(256 rows x 256 cols per pair) = sum_k [A1 | A2][row, k] * B[k, col]
 //   pass 2  : A1 = V, B = W            epilogue  Xb = (X - D) * inv_vn, row quad partials, sum Xb^2
 //   Vb      : A1 = V, A2 = Xb, B = [r L Binv ; -W^T]   epilogue  out = D
 //   generic : out = alpha * (X - A M)
-// A is K-major (row-major, contraction along columns): TMA box {16 floats, 128 rows} with SWIZZLE_64B, UMMA
-// layout SWIZZLE_64B, SBO = 512 B (8 rows x 64 B), +32 B per K = 8 step.  B is MN-major exactly as in pass 1.
-// Same pipeline, converter and window/drain machinery as tc_pass1_kernel.
 // =====================================================================================================
 struct RowsParams {
   int64_t n;
   int K1, K2;          // contraction lengths of A1 and A2 (K2 may be 0)
   int ncols;           // columns of B / of the output
   int col_tiles;       // ceil(ncols / 256)
-  int64_t row_tiles;   // ceil(n / 128)
+  int64_t row_tiles;   // ceil(n / 256)
   // epilogue
   int mode;            // 0: out = alpha * (X - D) (+ quad / xb2 partials when quad_part != nullptr); 1: out = D
   const float* X; int64_t ldx;
@@ -324,172 +392,97 @@ struct RowsParams {
   const double* scal;  // mode 0: alpha = 1 / scal[VN] when set, else alpha_host
   float alpha_host;
   float* quad_part;    // [col_tiles * 2][n]
-  double* xb2_part;    // [units * 8]
+  double* xb2_part;    // [units * 16]
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  TcShared* sm = reinterpret_cast<TcShared*>(base + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sm->full[s], 1);
-      mbar_init(&sm->conv[s], 4);
-      mbar_init(&sm->empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&sm->tfull[b], 1);
-      mbar_init(&sm->tempty[b], 8);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(&sm->tmem_base, 512);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = sm->tmem_base;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  uint32_t tmem;
+  TcShared* sm = tc_prologue(base, tmem);
   const int64_t nunits = p.row_tiles * p.col_tiles;
   const int nst1 = (p.K1 + TBK - 1) / TBK, nst2 = (p.K2 + TBK - 1) / TBK;
   const int nst = nst1 + nst2;
 
   if (warp < 4) {
     setmaxnreg_dec<40>();
-    if (warp == 0) {
-      if (lane == 0) {
-        tma_prefetch_desc(&tmA1);
-        tma_prefetch_desc(&tmA2);
-        tma_prefetch_desc(&tmB);
-        uint32_t it = 0;
-        for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
-          const int64_t rt = u / p.col_tiles;
-          const int ct = (int)(u - rt * p.col_tiles);
-          const int row = (int)(rt * TM);
-          for (int st = 0; st < nst; ++st, ++it) {
-            const int s = it % kStages;
-            mbar_wait(&sm->empty[s], ((it / kStages) & 1) ^ 1);
-            uint8_t* dst = base + s * kStageBytes;
-            mbar_arrive_expect_tx(&sm->full[s], kRawBytes);
-            int kb;   // row of B where this k-block starts
-            if (st < nst1) {
-              tma_load_2d(dst, &tmA1, st * TBK, row, &sm->full[s]);
-              kb = st * TBK;
-            } else {
-              tma_load_2d(dst, &tmA2, (st - nst1) * TBK, row, &sm->full[s]);
-              kb = p.K1 + (st - nst1) * TBK;
-            }
-#pragma unroll
-            for (int g = 0; g < TN / 32; ++g)
-              tma_load_2d(dst + kABytes + g * (TBK * 128), &tmB, ct * TN + g * 32, kb, &sm->full[s]);
+    if (warp == 0 && lane == 0) {
+      PROF_DECL;
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB);
+      uint32_t it = 0;
+      for (int64_t u = pair; u < nunits; u += npairs) {
+        const int64_t rt = u / p.col_tiles;
+        const int ct = (int)(u - rt * p.col_tiles);
+        const int row = (int)(rt * TM) + (int)rank * HM;
+        const int bcol = ct * TN + (int)rank * HN;
+        for (int st = 0; st < nst; ++st, ++it) {
+          const int s = it % kStages;
+          PROF_WAIT(pw0, mbar_wait(&sm->empty[s], ((it / kStages) & 1) ^ 1));
+          uint8_t* dst = base + s * kStageBytes;
+          mbar_arrive_expect_tx(&sm->full[s], kRawBytes);
+          int kb;   // row of B where this k-block starts
+          if (st < nst1) {
+            tma_load_2d(dst, &tmA1, st * TBK, row, &sm->full[s]);
+            kb = st * TBK;
+          } else {
+            tma_load_2d(dst, &tmA2, (st - nst1) * TBK, row, &sm->full[s]);
+            kb = p.K1 + (st - nst1) * TBK;
           }
+#pragma unroll
+          for (int g = 0; g < HN / 32; ++g)
+            tma_load_2d(dst + kABytes + g * (TBK * 128), &tmB, bcol + g * 32, kb, &sm->full[s]);
         }
       }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_tf32(TM, TN, false, true);
-        uint32_t it = 0, wc = 0;
-        for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
-          for (int st0 = 0; st0 < nst; st0 += kWinStages, ++wc) {
-            const uint32_t buf = wc & 1;
-            mbar_wait(&sm->tempty[buf], ((wc >> 1) & 1) ^ 1);
-            tcgen05_fence_after();
-            const uint32_t d = tmem + buf * TN;
-            const int wst = min(kWinStages, nst - st0);
-            for (int j = 0; j < wst; ++j, ++it) {
-              const int s = it % kStages;
-              mbar_wait(&sm->conv[s], (it / kStages) & 1);
-              tcgen05_fence_after();
-              const uint32_t a_hi = smem_u32(base + s * kStageBytes), b_hi = a_hi + kABytes;
-              const uint32_t a_lo = a_hi + kRawBytes, b_lo = a_lo + kABytes;
-#pragma unroll
-              for (int kk = 0; kk < TBK / 8; ++kk) {
-                const uint64_t dah = umma_desc(a_hi + kk * 32, 16, 512, kLayoutSw64);
-                const uint64_t dal = umma_desc(a_lo + kk * 32, 16, 512, kLayoutSw64);
-                const uint64_t dbh = umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
-                const uint64_t dbl = umma_desc(b_lo + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
-                umma_tf32(d, dah, dbh, idesc, (j | kk) != 0);
-                umma_tf32(d, dah, dbl, idesc, 1);
-                umma_tf32(d, dal, dbh, idesc, 1);
-              }
-              umma_commit(&sm->empty[s]);
-            }
-            umma_commit(&sm->tfull[buf]);
-          }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      PROF_DECL;
+      uint32_t it = 0, wc = 0;
+      for (int64_t u = pair; u < nunits; u += npairs) {
+        for (int st0 = 0; st0 < nst; st0 += kWin, ++wc) {
+          const uint32_t buf = wc & 1;
+          PROF_WAIT(pw0, mbar_wait_cluster(&sm->tempty[buf], ((wc >> 1) & 1) ^ 1));
+          const int wst = min(kWin, nst - st0);
+          issue_window<false>(base, sm, tmem + buf * TN, it, wst, pw1);
+          umma_commit_pair(&sm->tfull[buf], 3);
+          it += wst;
         }
       }
     }
   } else if (warp < 8) {
     setmaxnreg_dec<96>();
-    const int t = threadIdx.x - 128;
+    PROF_DECL;
+    const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
     uint32_t it = 0;
-    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
-      for (int st = 0; st < nst; ++st, ++it) {
-        const int s = it % kStages;
-        mbar_wait(&sm->full[s], (it / kStages) & 1);
-        float4* raw = reinterpret_cast<float4*>(base + s * kStageBytes);
-        float4* lo = reinterpret_cast<float4*>(base + s * kStageBytes + kRawBytes);
-#pragma unroll 4
-        for (int i = t; i < kRawBytes / 16; i += 128) {
-          const float4 v = raw[i];
-          float4 l;
-#if GPP_TC_STORE_HI
-          float4 h;
-          split_tf32(v.x, h.x, l.x);
-          split_tf32(v.y, h.y, l.y);
-          split_tf32(v.z, h.z, l.z);
-          split_tf32(v.w, h.w, l.w);
-          raw[i] = h;
-#else
-          l.x = tf32_rn(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
-          l.y = tf32_rn(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
-          l.z = tf32_rn(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
-          l.w = tf32_rn(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-#endif
-          lo[i] = l;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm->conv[s]);
-      }
-    }
+    for (int64_t u = pair; u < nunits; u += npairs)
+      for (int st = 0; st < nst; ++st, ++it) convert_stage(base, sm, conv0, it, pw0);
   } else {
     setmaxnreg_inc<184>();
-    const int q = warp & 3;
-    const int half = (warp - 8) >> 2;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    PROF_DECL;
+    const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
+    const int q = warp & 3, half = (warp - 8) >> 2;
     uint32_t wc = 0;
     float alpha = p.alpha_host;
     if (p.mode == 0 && p.scal) alpha = (float)(1.0 / p.scal[GPP_S_VN]);
-    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+    for (int64_t u = pair; u < nunits; u += npairs) {
       const int64_t rt = u / p.col_tiles;
       const int ct = (int)(u - rt * p.col_tiles);
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-      for (int st0 = 0; st0 < nst; st0 += kWinStages, ++wc) {
-        const uint32_t buf = wc & 1;
-        mbar_wait(&sm->tfull[buf], (wc >> 1) & 1);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tmem_ld_32x32(tmem + lane_addr + buf * TN + half * 128 + c * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm->tempty[buf]);
-      }
-      // ---- epilogue for this unit
-      const int64_t row = rt * TM + q * 32 + lane;
+      for (int st0 = 0; st0 < nst; st0 += kWin, ++wc) drain_window(sm, tmem, tempty0, wc, acc, pw0);
+      // ---- epilogue for this unit: this CTA's 128 rows
+      const int64_t row = rt * TM + rank * HM + q * 32 + lane;
       const int col0 = ct * TN + half * 128;
-      float quad = 0.f, xb2 = 0.f;
+      float xb2 = 0.f;
       if (row < p.n) {
         if (p.mode == 0) {
+          float quad = 0.f;
           const float* xr = p.X + row * p.ldx + col0;
           float* orow = p.out + row * p.ldo + col0;
 #pragma unroll
@@ -519,13 +512,11 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
       if (p.mode == 0 && p.xb2_part) {
         const float s = warp_sum(xb2);
-        if (lane == 0) p.xb2_part[u * 8 + (warp - 8)] = (double)s;
+        if (lane == 0) p.xb2_part[u * 16 + rank * 8 + (warp - 8)] = (double)s;
       }
     }
   }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  tc_epilogue(tmem);
 }
 
 // Bstk (Q + L rows, Q cols) = [ (v0/vn) L_true Binv ; -W^T ]
@@ -581,25 +572,61 @@ int make_map_2d(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, in
   return GPP_OK;
 }
 
+// CTA pairs that can be co-resident (persistent grid = 2 x this); B200: 148 SMs -> up to 74 pairs.
+template <typename K>
+int pair_count(K kernel) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (unsigned)sm_count());
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = sm_count() / 2;
+  }
+  return n;
+}
+
+int pass1_pairs() {
+  static int n = 0;
+  if (n == 0) {
+    cudaFuncSetAttribute(tc_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    n = pair_count(tc_pass1_kernel);
+  }
+  return n;
+}
+int rows_pairs() {
+  static int n = 0;
+  if (n == 0) {
+    cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    n = pair_count(tc_rows_kernel);
+  }
+  return n;
+}
+
 void pass1_geometry(int64_t n, int Q, int L, Pass1Params& p) {
   p.n = n; p.Q = Q; p.L = L;
   p.tm_count = (int)ceil_div(Q, TM);
-  p.tiles_g = 0;
-  for (int t = 0; t < p.tm_count; ++t) p.tiles_g += (t >> 1) + 1;
+  p.tiles_g = p.tm_count * (p.tm_count + 1) / 2;
   p.tn_c = (int)ceil_div(L, TN);
   p.tiles = p.tiles_g + p.tm_count * p.tn_c;
-  // choose the split count: best wave efficiency on the persistent grid, >= 1024 rows per split, <= 512 MB partials
-  const int sms = sm_count();
-  const int64_t max_by_rows = n / 1024 > 1 ? n / 1024 : 1;
-  const int64_t max_by_ws = (int64_t)(512ll << 20) / ((int64_t)p.tiles * TM * TN * 4);
+  // choose the split count: best wave efficiency on the persistent grid of CTA pairs, >= 512 rows per split,
+  // <= 1 GB of partial tiles
+  const int pairs = pass1_pairs();
+  const int64_t max_by_rows = n / 512 > 1 ? n / 512 : 1;
+  const int64_t max_by_ws = (int64_t)(1024ll << 20) / ((int64_t)p.tiles * TM * TN * 4);
   int64_t smax = max_by_rows < max_by_ws ? max_by_rows : max_by_ws;
   if (smax < 1) smax = 1;
-  if (smax > 64) smax = 64;
+  if (smax > 2 * pairs) smax = 2 * pairs;
   int best = 1;
   double best_eff = 0;
   for (int s = 1; s <= smax; ++s) {
     const int64_t units = (int64_t)p.tiles * s;
-    const double eff = (double)units / (double)(ceil_div(units, sms) * sms);
+    const double eff = (double)units / (double)(ceil_div(units, pairs) * pairs);
     if (eff > best_eff + 0.02) {   // prefer fewer splits unless efficiency improves by > 2 %
       best_eff = eff;
       best = s;
@@ -610,6 +637,12 @@ void pass1_geometry(int64_t n, int Q, int L, Pass1Params& p) {
 }
 
 }  // namespace
+
+#ifdef GPP_TC_PROF
+extern "C" int gpp_debug_prof(unsigned long long* out /* [512][16] */) {
+  return cudaMemcpyFromSymbol(out, g_prof, sizeof(g_prof)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 bool tc_pass1_supported(int64_t n, int Q, int L) { return Q >= 128 && n >= 512 && encode_fn() != nullptr; }
 
@@ -633,16 +666,11 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
   GPP_TRY(make_map_2d(&tmV, V, n, Q, ldv, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   if (L > 0) GPP_TRY(make_map_2d(&tmX, X, n, L, ldx, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   else tmX = tmV;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GPP_CUDA(cudaFuncSetAttribute(tc_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
   const int nunits = p.tiles * p.splits;
-  const int grid = nunits < sm_count() ? nunits : sm_count();
-  tc_pass1_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(tmV, tmX, p);
+  const int pairs = nunits < pass1_pairs() ? nunits : pass1_pairs();
+  tc_pass1_kernel<<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmV, tmX, p);
   GPP_LAUNCH_CHECK();
-  tc_reduce_kernel<<<p.tiles, 256, 0, st>>>(p, GC, ldgc);
+  tc_reduce_kernel<<<p.tiles * 8, 256, 0, st>>>(p, GC, ldgc);
   GPP_LAUNCH_CHECK();
   dim3 mg((unsigned)ceil_div(Q, 32), (unsigned)ceil_div(Q, 32));
   tc_mirror_kernel<<<mg, 256, 0, st>>>(GC, ldgc, Q);
@@ -654,28 +682,23 @@ bool tc_rows_supported(int64_t n, int K, int ncols) { return n >= 512 && K >= 64
 
 size_t tc_xb_workspace_bytes(int64_t n, int L) {
   const int64_t col_tiles = ceil_div(L, TN), row_tiles = ceil_div(n, TM);
-  return align_up((size_t)col_tiles * 2 * n * sizeof(float), 256) + (size_t)row_tiles * col_tiles * 8 * sizeof(double);
+  return align_up((size_t)col_tiles * 2 * n * sizeof(float), 256) + (size_t)row_tiles * col_tiles * 16 * sizeof(double);
 }
 
 static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, int64_t lda2, int K2, const float* B,
                        int64_t ldb, int64_t n, int ncols, RowsParams& p, cudaStream_t st) {
   CUtensorMap tmA1, tmA2, tmB;
-  GPP_TRY(make_map_2d(&tmA1, A1, n, K1, lda1, TBK, TM, CU_TENSOR_MAP_SWIZZLE_64B));
-  if (K2 > 0) GPP_TRY(make_map_2d(&tmA2, A2, n, K2, lda2, TBK, TM, CU_TENSOR_MAP_SWIZZLE_64B));
+  GPP_TRY(make_map_2d(&tmA1, A1, n, K1, lda1, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
+  if (K2 > 0) GPP_TRY(make_map_2d(&tmA2, A2, n, K2, lda2, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
   else tmA2 = tmA1;
   GPP_TRY(make_map_2d(&tmB, B, (int64_t)K1 + K2, ncols, ldb, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   p.n = n; p.K1 = K1; p.K2 = K2; p.ncols = ncols;
   p.col_tiles = (int)ceil_div(ncols, TN);
   p.row_tiles = ceil_div(n, TM);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GPP_CUDA(cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
-  }
   const int64_t nunits = p.row_tiles * p.col_tiles;
-  const int grid = (int)(nunits < sm_count() ? nunits : sm_count());
-  if (grid <= 0) return GPP_OK;
-  tc_rows_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(tmA1, tmA2, tmB, p);
+  const int pairs = (int)(nunits < rows_pairs() ? nunits : rows_pairs());
+  if (pairs <= 0) return GPP_OK;
+  tc_rows_kernel<<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmA1, tmA2, tmB, p);
   GPP_LAUNCH_CHECK();
   return GPP_OK;
 }
@@ -697,7 +720,7 @@ int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const
     p.xb2_part = reinterpret_cast<double*>(static_cast<char*>(ws) + align_up((size_t)col_tiles * 2 * n * sizeof(float), 256));
   }
   GPP_TRY(launch_rows(V, ldv, Q, nullptr, 0, 0, W, ldw, n, L, p, st));
-  if (nll) GPP_TRY(launch_xb_finalize(p.quad_part, (int)(col_tiles * 2), n, p.xb2_part, row_tiles * col_tiles * 8, scal, nll, st));
+  if (nll) GPP_TRY(launch_xb_finalize(p.quad_part, (int)(col_tiles * 2), n, p.xb2_part, row_tiles * col_tiles * 16, scal, nll, st));
   return GPP_OK;
 }
 

@@ -148,16 +148,20 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
-// arrive on an mbarrier that may live in the peer CTA (address from mapa_u32); release at cluster scope
+// arrive on an mbarrier that may live in the peer CTA (address from mapa_u32).  Default (.release.cta) semantics on
+// purpose: ".release.cluster" compiles to MEMBAR.ALL.GPU in front of every arrive (measured: it made the converter
+// warps the bottleneck of the pair kernels); what the consumers of these barriers read is ordered by
+// fence.proxy.async (shared-memory tiles -> tensor core) and tcgen05.fence (TMEM), not by the arrive itself.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
+// wait on a barrier that also receives arrivals from the peer CTA (same instruction as mbar_wait; kept separate
+// so the cross-CTA waits are easy to find)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
