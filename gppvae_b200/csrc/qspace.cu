@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "gemm_simt.cuh"
 #include "kernels.h"
 
 namespace gpp {
@@ -197,29 +198,129 @@ __device__ __forceinline__ void invert64(const Block64& As, Block64& Xs, float (
   }
 }
 
-// Panel step of the blocked Cholesky.  D: the 64 x 64 diagonal block (read only here), Ld: where L11 goes,
-// P: the rows below it (ld = lda), overwritten with L21.  Grid = 1 + ceil(rows_below / 64).
-__global__ void __launch_bounds__(kPotfThreads) chol_panel_kernel(const float* __restrict__ D, float* __restrict__ P,
-                                                                  int64_t lda, int rows_below,
-                                                                  float* __restrict__ Ld) {
-  __shared__ Block64 As;
-  __shared__ Block64 Xs;
-  __shared__ float rd16[SB];
-  __shared__ float li16[NB / SB][SB][SB + 1];
+// One step of the blocked Cholesky with look-ahead, ONE kernel per 64-wide panel j:
+//   panel CTAs (blockIdx < nb - j; CTA 0 = the diagonal block only, CTA b >= 1 = block row j + b):
+//       apply the rank-64 update of panel j-1 to their own 64 x 64 blocks of column j (the diagonal block redundantly
+//       in every CTA), factor the diagonal block (redundantly: it removes a launch and a grid-wide dependency from the
+//       critical path), CTA 0 parks L11 in Ld, CTA b solves X L11^T = A21 for its rows;
+//   wide CTAs (the rest): A[i, c] -= L[i, j-1] L[c, j-1]^T on 128 x 128 tiles of the columns >= j + 1 (lower tiles),
+//       i.e. the trailing update of the PREVIOUS panel, which is off the critical path of this step.
+// Column block c thus receives panel k < c - 1 from the wide CTAs of step k + 1 and panel c - 1 from its own panel
+// CTAs; both roles only read what earlier launches finished (column j-1) and write disjoint blocks.
+struct StepSmem {
+  Block64 As, Xs, LsT, PsT;   // diagonal block, this CTA's block row, L[j, j-1]^T, L[j+b, j-1]^T
+  float rd16[SB];
+  float li16[NB / SB][SB][SB + 1];
+};
+constexpr size_t kStepSmemBytes = sizeof(StepSmem) > sizeof(TileSmem) ? sizeof(StepSmem) : sizeof(TileSmem);
+
+__global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __restrict__ Bm, int Qp, int j,
+                                                                 float* __restrict__ Ld) {
+  extern __shared__ __align__(16) uint8_t step_smem[];
   const int tid = threadIdx.x;
-  for (int e = tid; e < NB * NB; e += kPotfThreads) As.a[e >> 6][e & 63] = D[(int64_t)(e >> 6) * lda + (e & 63)];
-  for (int e = tid; e < (NB / SB) * SB * (SB + 1); e += kPotfThreads) (&li16[0][0][0])[e] = 0.f;
-  const int row0 = ((int)blockIdx.x - 1) * NB;
-  if (blockIdx.x > 0) {
+  const int nb = Qp / NB, k0 = j * NB;
+  const int npanel = nb - j;
+  if ((int)blockIdx.x >= npanel) {
+    // ------------------------------------------------------------ wide role: trailing update of panel j - 1
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(step_smem);
+    const int widx = (int)blockIdx.x - npanel;
+    int ti = (int)((sqrtf(8.f * (float)widx + 1.f) - 1.f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= widx) ++ti;
+    while (ti * (ti + 1) / 2 > widx) --ti;
+    const int tc = widx - ti * (ti + 1) / 2;
+    const int t0 = k0 + NB;
+    const int r0 = t0 + ti * BM, c0 = t0 + tc * BN;
+    Operand A, B;
+    A.base = Bm + (int64_t)r0 * Qp + (k0 - NB); A.ld = Qp; A.mn_valid = min(BM, Qp - r0);
+    B.base = Bm + (int64_t)c0 * Qp + (k0 - NB); B.ld = Qp; B.mn_valid = min(BN, Qp - c0);
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) acc[i][jj] = 0.f;
+    tile_mainloop<false, false>(A, B, NB, sm, acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = acc_row(i);
+      if (r >= A.mn_valid) continue;
+      float* crow = Bm + (int64_t)(r0 + r) * Qp + c0;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int c = acc_col(jj * 4);
+        if (c >= B.mn_valid) continue;   // mn_valid is a multiple of 64, so a float4 never straddles the edge
+        float4* c4 = reinterpret_cast<float4*>(crow + c);
+        float4 v = *c4;
+        v.x -= acc[i][jj * 4 + 0]; v.y -= acc[i][jj * 4 + 1]; v.z -= acc[i][jj * 4 + 2]; v.w -= acc[i][jj * 4 + 3];
+        *c4 = v;
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------- panel role
+  StepSmem& S = *reinterpret_cast<StepSmem*>(step_smem);
+  const int b = (int)blockIdx.x;
+  const float* D = Bm + (int64_t)k0 * (Qp + 1);
+  float* P = Bm + (int64_t)(k0 + b * NB) * Qp + k0;   // block (j + b, j); unused for b == 0
+  for (int e = tid; e < NB * NB; e += kPotfThreads) S.As.a[e >> 6][e & 63] = D[(int64_t)(e >> 6) * Qp + (e & 63)];
+  for (int e = tid; e < (NB / SB) * SB * (SB + 1); e += kPotfThreads) (&S.li16[0][0][0])[e] = 0.f;
+  if (b > 0)
+    for (int e = tid; e < NB * NB; e += kPotfThreads) S.Xs.a[e >> 6][e & 63] = P[(int64_t)(e >> 6) * Qp + (e & 63)];
+  if (j > 0) {
+    // rank-64 update from panel j - 1:  D -= Lj Lj^T,  P -= Lp Lj^T   (operands staged transposed: [k][row])
+    const float* Lj = D - NB;
+    const float* Lp = P - NB;
     for (int e = tid; e < NB * NB; e += kPotfThreads) {
       const int r = e >> 6, c = e & 63;
-      Xs.a[r][c] = (row0 + r < rows_below) ? P[(int64_t)(row0 + r) * lda + c] : 0.f;
+      S.LsT.a[c][r] = Lj[(int64_t)r * Qp + c];
+      if (b > 0) S.PsT.a[c][r] = Lp[(int64_t)r * Qp + c];
     }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    float ad[4][4], ap[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) ad[i][jj] = ap[i][jj] = 0.f;
+    if (b > 0) {
+#pragma unroll 8
+      for (int k = 0; k < NB; ++k) {
+        const float4 l4 = *reinterpret_cast<const float4*>(&S.LsT.a[k][tx * 4]);
+        const float4 a4 = *reinterpret_cast<const float4*>(&S.LsT.a[k][ty * 4]);
+        const float4 p4 = *reinterpret_cast<const float4*>(&S.PsT.a[k][ty * 4]);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w}, pv[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            ad[i][jj] = fmaf(av[i], lv[jj], ad[i][jj]);
+            ap[i][jj] = fmaf(pv[i], lv[jj], ap[i][jj]);
+          }
+      }
+    } else {
+#pragma unroll 8
+      for (int k = 0; k < NB; ++k) {
+        const float4 l4 = *reinterpret_cast<const float4*>(&S.LsT.a[k][tx * 4]);
+        const float4 a4 = *reinterpret_cast<const float4*>(&S.LsT.a[k][ty * 4]);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) ad[i][jj] = fmaf(av[i], lv[jj], ad[i][jj]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        S.As.a[ty * 4 + i][tx * 4 + jj] -= ad[i][jj];
+        if (b > 0) S.Xs.a[ty * 4 + i][tx * 4 + jj] -= ap[i][jj];
+      }
   }
   __syncthreads();
-  factor64(As, rd16, li16);
-  if (blockIdx.x == 0) {
-    for (int e = tid; e < NB * NB; e += kPotfThreads) Ld[e] = As.a[e >> 6][e & 63];
+  factor64(S.As, S.rd16, S.li16);
+  if (b == 0) {
+    float* dst = Ld + (size_t)j * NB * NB;
+    for (int e = tid; e < NB * NB; e += kPotfThreads) dst[e] = S.As.a[e >> 6][e & 63];
     return;
   }
   __syncthreads();
@@ -230,34 +331,31 @@ __global__ void __launch_bounds__(kPotfThreads) chol_panel_kernel(const float* _
       const int o = cb * SB;
       float t[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) t[j] = Xs.a[r][o + cq + j];
+      for (int jj = 0; jj < 4; ++jj) t[jj] = S.Xs.a[r][o + cq + jj];
       for (int k = 0; k < o; ++k) {
-        const float xk = Xs.a[r][k];
+        const float xk = S.Xs.a[r][k];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) t[j] = fmaf(-xk, As.a[o + cq + j][k], t[j]);
+        for (int jj = 0; jj < 4; ++jj) t[jj] = fmaf(-xk, S.As.a[o + cq + jj][k], t[jj]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) Xs.a[r][o + cq + j] = t[j];
+      for (int jj = 0; jj < 4; ++jj) S.Xs.a[r][o + cq + jj] = t[jj];
       __syncwarp();
       float tr[SB];
 #pragma unroll
-      for (int k = 0; k < SB; ++k) tr[k] = Xs.a[r][o + k];
+      for (int k = 0; k < SB; ++k) tr[k] = S.Xs.a[r][o + k];
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int jj = 0; jj < 4; ++jj) {
         float sx = 0.f;
 #pragma unroll
-        for (int k = 0; k < SB; ++k) sx = fmaf(tr[k], li16[cb][cq + j][k], sx);   // Li is lower: entries k > c are 0
-        Xs.a[r][o + cq + j] = sx;
+        for (int k = 0; k < SB; ++k) sx = fmaf(tr[k], S.li16[cb][cq + jj][k], sx);   // Li is lower: entries k > c are 0
+        S.Xs.a[r][o + cq + jj] = sx;
       }
       __syncwarp();
     }
   }
   __syncthreads();
-  for (int e = tid; e < NB * NB; e += kPotfThreads) {
-    const int r = e >> 6, c = e & 63;
-    if (row0 + r < rows_below) P[(int64_t)(row0 + r) * lda + c] = Xs.a[r][c];
-  }
+  for (int e = tid; e < NB * NB; e += kPotfThreads) P[(int64_t)(e >> 6) * Qp + (e & 63)] = S.Xs.a[e >> 6][e & 63];
 }
 
 // Linv diagonal blocks: one CTA per 64 x 64 diagonal factor (Ld[j]) -> Linv[j*64.., j*64..] (ld = ldd).
@@ -437,23 +535,20 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
   }
   GPP_CUDA(cudaMemsetAsync(Linv, 0, (size_t)Qp * Qp * sizeof(float), st));
 
-  // ---- blocked right-looking Cholesky: per 64-wide panel ONE fused kernel (diagonal factor + panel solve) and one
-  //      trailing update; the diagonal factors are parked in Ld so that no CTA reads a block another one rewrites
+  // ---- blocked Cholesky with look-ahead: ONE kernel per 64-wide panel (see chol_step_kernel); the diagonal factors
+  //      are parked in Ld so that no CTA reads a block another one rewrites
   float* Ld = reinterpret_cast<float*>(base + f.off_ld);
+  static bool step_attr = false;
+  if (!step_attr) {
+    GPP_CUDA(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepSmemBytes));
+    step_attr = true;
+  }
   for (int j = 0; j < nb; ++j) {
-    const int k0 = j * NB;
-    const int rem = Qp - k0 - NB;
-    const float* diag = Bm + (int64_t)k0 * (Qp + 1);
-    float* panel = Bm + (int64_t)(k0 + NB) * Qp + k0;  // A21, becomes L21 in place
-    chol_panel_kernel<<<1 + (rem > 0 ? (rem + NB - 1) / NB : 0), kPotfThreads, 0, st>>>(diag, panel, Qp, rem,
-                                                                                         Ld + (size_t)j * NB * NB);
+    const int npanel = nb - j;
+    const int trail = Qp - (j + 1) * NB;
+    const int T = j > 0 ? (trail + BM - 1) / BM : 0;
+    chol_step_kernel<<<npanel + T * (T + 1) / 2, kPotfThreads, kStepSmemBytes, st>>>(Bm, Qp, j, Ld);
     GPP_LAUNCH_CHECK();
-    if (rem <= 0) break;
-    GemmParams s{};
-    s.A = panel; s.lda = Qp; s.B = panel; s.ldb = Qp;
-    s.C = Bm + (int64_t)(k0 + NB) * (Qp + 1); s.ldc = Qp;
-    s.M = rem; s.N = rem; s.K = NB; s.M_last = -1; s.alpha = -1.f; s.beta = 1.f; s.lower_only = 1;
-    GPP_TRY(launch_gemm(s, false, false, 1, st));  // A22 -= L21 . L21^T (lower tiles)
   }
   diag_store_kernel<<<nb, kPotfThreads, 0, st>>>(Ld, Bm, Qp);
   GPP_LAUNCH_CHECK();
