@@ -51,7 +51,7 @@ extern "C" uint64_t gpp_launch_count(void) { return g_launches.load(std::memory_
 // ------------------------------------------------------------------ pass 1
 extern "C" size_t gpp_gram_workspace_bytes(int64_t n, int32_t Q, int32_t L) {
   const size_t a = tn_workspace_bytes(n, Q, Q, L, 1);
-  const size_t b = tc_pass1_supported(n, Q, L) ? tc_pass1_workspace_bytes(n, Q, L) : 0;
+  const size_t b = tc_pass1_supported(n, Q, L) ? tc_pass1_workspace_bytes(n, Q, L, false) : 0;
   return a > b ? a : b;
 }
 
@@ -64,7 +64,8 @@ extern "C" int gpp_gram_vtz(const float* V, int64_t ldv, const float* X, int64_t
   GPP_REQUIRE(mat_ok(GC, ldgc, (int64_t)Q + L), "gram_vtz: GC must be 16-byte aligned with ldgc >= Q + L");
   // large problems run on the tensor cores (3xTF32); tiles that cannot fill a 256 x 256 pair UMMA use the fp32 tile engine
   if (tc_pass1_supported(n, Q, L))
-    return launch_tc_pass1(V, ldv, X, ldx, n, Q, L, GC, ldgc, workspace, workspace_bytes, (cudaStream_t)stream);
+    return launch_tc_pass1(V, ldv, X, ldx, n, Q, L, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
   return launch_tn(V, ldv, Q, V, ldv, Q, X, ldx, L, n, 1, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes,
                    (cudaStream_t)stream);
 }

@@ -88,6 +88,9 @@ struct Pass1Params {
   int splits;
   int64_t rows_per_split;  // multiple of TBK
   float* partial;          // [tile][split][TM * TN]
+  float* G; int64_t ldg;   // V^T V  (not touched when tiles_g == 0)
+  float* C; int64_t ldc;   // V^T X
+  const double* scal_c;    // when set: C *= scal[V0] / scal[VN]
 };
 
 __device__ __forceinline__ void decode_tile(const Pass1Params& p, int tile, int& tm, int& tn, bool& is_c) {
@@ -335,7 +338,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
 
 // GC[r][c] = sum_s partial[tile][s][..] for every computed tile (fixed order, fp64 accumulation).
 // grid = tiles * 8: CTA (tile, j) reduces rows [32 j, 32 j + 32) of the tile.
-__global__ void __launch_bounds__(256) tc_reduce_kernel(Pass1Params p, float* __restrict__ GC, int64_t ldgc) {
+__global__ void __launch_bounds__(256) tc_reduce_kernel(Pass1Params p) {
   const int tile = blockIdx.x >> 3, rblk = blockIdx.x & 7;
   int tm, tn;
   bool is_c;
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(Pass1Params p, float* __
   const int ncols = is_c ? p.L : p.Q;
   const int col0 = tn * TN, row0 = tm * TM + rblk * 32;
   const float* src = p.partial + (size_t)tile * p.splits * (size_t)(TM * TN) + (size_t)rblk * 32 * TN;
+  const double scale = (is_c && p.scal_c) ? p.scal_c[GPP_S_V0] / p.scal_c[GPP_S_VN] : 1.0;
   for (int e = threadIdx.x; e < 32 * TN / 4; e += blockDim.x) {
     const int r = e / (TN / 4), c4 = (e - r * (TN / 4)) * 4;
     if (row0 + r >= p.Q || col0 + c4 >= ncols) continue;
@@ -351,8 +355,9 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(Pass1Params p, float* __
       const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * (TM * TN) + r * TN + c4);
       s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
     }
-    float* dst = GC + (int64_t)(row0 + r) * ldgc + (is_c ? p.Q : 0) + col0 + c4;
-    *reinterpret_cast<float4*>(dst) = make_float4((float)s0, (float)s1, (float)s2, (float)s3);
+    float* dst = (is_c ? p.C + (int64_t)(row0 + r) * p.ldc : p.G + (int64_t)(row0 + r) * p.ldg) + col0 + c4;
+    *reinterpret_cast<float4*>(dst) =
+        make_float4((float)(scale * s0), (float)(scale * s1), (float)(scale * s2), (float)(scale * s3));
   }
 }
 
@@ -386,7 +391,13 @@ struct RowsParams {
   int col_tiles;       // ceil(ncols / 256)
   int64_t row_tiles;   // ceil(n / 256)
   // epilogue
-  int mode;            // 0: out = alpha * (X - D) (+ quad / xb2 partials when quad_part != nullptr); 1: out = D
+  int mode;            // 0: out = alpha * (X - D) (+ quad / xb2 partials when quad_part != nullptr); 1: out = alpha * D
+  // batched blocks of larger matrices (Q-space solves): batch b reads A rows from a_row0 + b a_row_step and A columns
+  // (= k) from a_k0 + b a_k_step, B rows (= k) from b_k0 + b b_k_step and B columns from b_col0 + b b_col_step, and
+  // writes out + b out_step; the last batch has n_last (<= n) rows.  tri_a: A[row, k] = 0 for k > row (stop the
+  // contraction at the row tile's end); tri_b: B[k, col] = 0 for k < col (start it at the column tile's start).
+  int batches, a_row0, a_row_step, a_k0, a_k_step, b_k0, b_k_step, b_col0, b_col_step, tri_a, tri_b;
+  int64_t out_step, n_last;
   const float* X; int64_t ldx;
   float* out; int64_t ldo;
   const double* scal;  // mode 0: alpha = 1 / scal[VN] when set, else alpha_host
@@ -394,6 +405,22 @@ struct RowsParams {
   float* quad_part;    // [col_tiles * 2][n]
   double* xb2_part;    // [units * 16]
 };
+
+struct RowsUnit {
+  int batch, ct, k_begin, k_end;   // stage range [k_begin, k_end) of this unit
+  int64_t rt;
+};
+__device__ __forceinline__ RowsUnit rows_unit(const RowsParams& p, int64_t u, int nst) {
+  RowsUnit r;
+  const int64_t per = p.row_tiles * p.col_tiles;
+  r.batch = (int)(u / per);
+  const int64_t v = u - (int64_t)r.batch * per;
+  r.rt = v / p.col_tiles;
+  r.ct = (int)(v - r.rt * p.col_tiles);
+  r.k_begin = p.tri_b ? r.ct * (TN / TBK) : 0;
+  r.k_end = p.tri_a ? min(nst, (int)(r.rt + 1) * (TM / TBK)) : nst;
+  return r;
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -405,7 +432,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   uint32_t tmem;
   TcShared* sm = tc_prologue(base, tmem);
-  const int64_t nunits = p.row_tiles * p.col_tiles;
+  const int64_t nunits = p.row_tiles * p.col_tiles * p.batches;
   const int nst1 = (p.K1 + TBK - 1) / TBK, nst2 = (p.K2 + TBK - 1) / TBK;
   const int nst = nst1 + nst2;
 
@@ -418,19 +445,19 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       tma_prefetch_desc(&tmB);
       uint32_t it = 0;
       for (int64_t u = pair; u < nunits; u += npairs) {
-        const int64_t rt = u / p.col_tiles;
-        const int ct = (int)(u - rt * p.col_tiles);
-        const int row = (int)(rt * TM) + (int)rank * HM;
-        const int bcol = ct * TN + (int)rank * HN;
-        for (int st = 0; st < nst; ++st, ++it) {
+        const RowsUnit un = rows_unit(p, u, nst);
+        const int row = p.a_row0 + un.batch * p.a_row_step + (int)(un.rt * TM) + (int)rank * HM;
+        const int bcol = p.b_col0 + un.batch * p.b_col_step + un.ct * TN + (int)rank * HN;
+        const int ak0 = p.a_k0 + un.batch * p.a_k_step, bk0 = p.b_k0 + un.batch * p.b_k_step;
+        for (int st = un.k_begin; st < un.k_end; ++st, ++it) {
           const int s = it % kStages;
           PROF_WAIT(pw0, mbar_wait(&sm->empty[s], ((it / kStages) & 1) ^ 1));
           uint8_t* dst = base + s * kStageBytes;
           mbar_arrive_expect_tx(&sm->full[s], kRawBytes);
           int kb;   // row of B where this k-block starts
           if (st < nst1) {
-            tma_load_2d(dst, &tmA1, st * TBK, row, &sm->full[s]);
-            kb = st * TBK;
+            tma_load_2d(dst, &tmA1, ak0 + st * TBK, row, &sm->full[s]);
+            kb = bk0 + st * TBK;
           } else {
             tma_load_2d(dst, &tmA2, (st - nst1) * TBK, row, &sm->full[s]);
             kb = p.K1 + (st - nst1) * TBK;
@@ -444,10 +471,11 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       PROF_DECL;
       uint32_t it = 0, wc = 0;
       for (int64_t u = pair; u < nunits; u += npairs) {
-        for (int st0 = 0; st0 < nst; st0 += kWin, ++wc) {
+        const RowsUnit un = rows_unit(p, u, nst);
+        for (int st0 = un.k_begin; st0 < un.k_end; st0 += kWin, ++wc) {
           const uint32_t buf = wc & 1;
           PROF_WAIT(pw0, mbar_wait_cluster(&sm->tempty[buf], ((wc >> 1) & 1) ^ 1));
-          const int wst = min(kWin, nst - st0);
+          const int wst = min(kWin, un.k_end - st0);
           issue_window<false>(base, sm, tmem + buf * TN, it, wst, pw1);
           umma_commit_pair(&sm->tfull[buf], 3);
           it += wst;
@@ -459,8 +487,10 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     PROF_DECL;
     const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
     uint32_t it = 0;
-    for (int64_t u = pair; u < nunits; u += npairs)
-      for (int st = 0; st < nst; ++st, ++it) convert_stage(base, sm, conv0, it, pw0);
+    for (int64_t u = pair; u < nunits; u += npairs) {
+      const RowsUnit un = rows_unit(p, u, nst);
+      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_stage(base, sm, conv0, it, pw0);
+    }
   } else {
     setmaxnreg_inc<184>();
     PROF_DECL;
@@ -470,17 +500,18 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     float alpha = p.alpha_host;
     if (p.mode == 0 && p.scal) alpha = (float)(1.0 / p.scal[GPP_S_VN]);
     for (int64_t u = pair; u < nunits; u += npairs) {
-      const int64_t rt = u / p.col_tiles;
-      const int ct = (int)(u - rt * p.col_tiles);
+      const RowsUnit un = rows_unit(p, u, nst);
+      const int64_t rt = un.rt;
+      const int ct = un.ct;
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-      for (int st0 = 0; st0 < nst; st0 += kWin, ++wc) drain_window(sm, tmem, tempty0, wc, acc, pw0);
+      for (int st0 = un.k_begin; st0 < un.k_end; st0 += kWin, ++wc) drain_window(sm, tmem, tempty0, wc, acc, pw0);
       // ---- epilogue for this unit: this CTA's 128 rows
       const int64_t row = rt * TM + rank * HM + q * 32 + lane;
       const int col0 = ct * TN + half * 128;
       float xb2 = 0.f;
-      if (row < p.n) {
+      if (row < (un.batch == p.batches - 1 ? p.n_last : p.n)) {
         if (p.mode == 0) {
           float quad = 0.f;
           const float* xr = p.X + row * p.ldx + col0;
@@ -503,11 +534,12 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           }
           if (p.quad_part) p.quad_part[(int64_t)(ct * 2 + half) * p.n + row] = quad;
         } else {
-          float* orow = p.out + row * p.ldo + col0;
+          float* orow = p.out + un.batch * p.out_step + row * p.ldo + col0;
 #pragma unroll
           for (int i = 0; i < 128; i += 4)
             if (col0 + i < p.ncols)
-              *reinterpret_cast<float4*>(orow + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+              *reinterpret_cast<float4*>(orow + i) =
+                  make_float4(alpha * acc[i], alpha * acc[i + 1], alpha * acc[i + 2], alpha * acc[i + 3]);
         }
       }
       if (p.mode == 0 && p.xb2_part) {
@@ -608,10 +640,10 @@ int rows_pairs() {
   return n;
 }
 
-void pass1_geometry(int64_t n, int Q, int L, Pass1Params& p) {
+void pass1_geometry(int64_t n, int Q, int L, bool skip_g, Pass1Params& p) {
   p.n = n; p.Q = Q; p.L = L;
   p.tm_count = (int)ceil_div(Q, TM);
-  p.tiles_g = p.tm_count * (p.tm_count + 1) / 2;
+  p.tiles_g = skip_g ? 0 : p.tm_count * (p.tm_count + 1) / 2;
   p.tn_c = (int)ceil_div(L, TN);
   p.tiles = p.tiles_g + p.tm_count * p.tn_c;
   // choose the split count: best wave efficiency on the persistent grid of CTA pairs, >= 512 rows per split,
@@ -646,22 +678,26 @@ extern "C" int gpp_debug_prof(unsigned long long* out /* [512][16] */) {
 
 bool tc_pass1_supported(int64_t n, int Q, int L) { return Q >= 128 && n >= 512 && encode_fn() != nullptr; }
 
-size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L) {
+size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g) {
   Pass1Params p;
-  pass1_geometry(n, Q, L, p);
+  pass1_geometry(n, Q, L, skip_g, p);
   return (size_t)p.tiles * p.splits * TM * TN * sizeof(float);
 }
 
-int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* GC,
-                    int64_t ldgc, void* ws, size_t ws_bytes, cudaStream_t st) {
+// G (Q x Q, optional) = V^T V and C (Q x L) = V^T X [* v0/vn when scal_c is set]; G == nullptr skips the Gram tiles.
+int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* G,
+                    int64_t ldg, float* C, int64_t ldc, const double* scal_c, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
   Pass1Params p;
-  pass1_geometry(n, Q, L, p);
+  pass1_geometry(n, Q, L, G == nullptr, p);
   const size_t need = (size_t)p.tiles * p.splits * TM * TN * sizeof(float);
   if (!ws || ws_bytes < need) {
     set_error("gram_vtz (tcgen05): workspace too small (%zu < %zu bytes)", ws_bytes, need);
     return GPP_ERR_WORKSPACE;
   }
+  if (p.tiles == 0) return GPP_OK;
   p.partial = static_cast<float*>(ws);
+  p.G = G; p.ldg = ldg; p.C = C; p.ldc = ldc; p.scal_c = scal_c;
   CUtensorMap tmV, tmX;
   GPP_TRY(make_map_2d(&tmV, V, n, Q, ldv, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   if (L > 0) GPP_TRY(make_map_2d(&tmX, X, n, L, ldx, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
@@ -670,11 +706,13 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
   const int pairs = nunits < pass1_pairs() ? nunits : pass1_pairs();
   tc_pass1_kernel<<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmV, tmX, p);
   GPP_LAUNCH_CHECK();
-  tc_reduce_kernel<<<p.tiles * 8, 256, 0, st>>>(p, GC, ldgc);
+  tc_reduce_kernel<<<p.tiles * 8, 256, 0, st>>>(p);
   GPP_LAUNCH_CHECK();
-  dim3 mg((unsigned)ceil_div(Q, 32), (unsigned)ceil_div(Q, 32));
-  tc_mirror_kernel<<<mg, 256, 0, st>>>(GC, ldgc, Q);
-  GPP_LAUNCH_CHECK();
+  if (G) {
+    dim3 mg((unsigned)ceil_div(Q, 32), (unsigned)ceil_div(Q, 32));
+    tc_mirror_kernel<<<mg, 256, 0, st>>>(G, ldg, Q);
+    GPP_LAUNCH_CHECK();
+  }
   return GPP_OK;
 }
 
@@ -685,6 +723,21 @@ size_t tc_xb_workspace_bytes(int64_t n, int L) {
   return align_up((size_t)col_tiles * 2 * n * sizeof(float), 256) + (size_t)row_tiles * col_tiles * 16 * sizeof(double);
 }
 
+static int launch_rows_maps(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB, int64_t n,
+                            int K1, int K2, int ncols, RowsParams& p, cudaStream_t st) {
+  p.n = n; p.K1 = K1; p.K2 = K2; p.ncols = ncols;
+  if (p.batches <= 0) p.batches = 1;
+  if (p.n_last <= 0) p.n_last = n;
+  p.col_tiles = (int)ceil_div(ncols, TN);
+  p.row_tiles = ceil_div(n, TM);
+  const int64_t nunits = p.row_tiles * p.col_tiles * p.batches;
+  const int pairs = (int)(nunits < rows_pairs() ? nunits : rows_pairs());
+  if (pairs <= 0) return GPP_OK;
+  tc_rows_kernel<<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmA1, tmA2, tmB, p);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
 static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, int64_t lda2, int K2, const float* B,
                        int64_t ldb, int64_t n, int ncols, RowsParams& p, cudaStream_t st) {
   CUtensorMap tmA1, tmA2, tmB;
@@ -692,15 +745,28 @@ static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, i
   if (K2 > 0) GPP_TRY(make_map_2d(&tmA2, A2, n, K2, lda2, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
   else tmA2 = tmA1;
   GPP_TRY(make_map_2d(&tmB, B, (int64_t)K1 + K2, ncols, ldb, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  p.n = n; p.K1 = K1; p.K2 = K2; p.ncols = ncols;
-  p.col_tiles = (int)ceil_div(ncols, TN);
-  p.row_tiles = ceil_div(n, TM);
-  const int64_t nunits = p.row_tiles * p.col_tiles;
-  const int pairs = (int)(nunits < rows_pairs() ? nunits : rows_pairs());
-  if (pairs <= 0) return GPP_OK;
-  tc_rows_kernel<<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmA1, tmA2, tmB, p);
-  GPP_LAUNCH_CHECK();
-  return GPP_OK;
+  return launch_rows_maps(tmA1, tmA2, tmB, n, K1, K2, ncols, p, st);
+}
+
+// Batched block GEMM inside larger row-major matrices (the Q-space solves):
+//   out_b (n x ncols) = alpha * A_b (n x K) . B_b (K x ncols),  b < g.batches,
+// A_b = Amat[a_row0 + b a_row_step .., a_k0 + b a_k_step ..], B_b = Bmat[b_k0 + b b_k_step .., b_col0 + b b_col_step ..],
+// out_b = out + b out_step.  Reads outside a block but inside its matrix only feed outputs that are not stored; reads
+// outside the matrix are zero (TMA), which is what the ragged last batch (n_last rows, at the matrix edge) relies on.
+bool tc_blockgemm_supported(int n, int K, int ncols) { return n >= 512 && K >= 64 && ncols >= 64 && encode_fn() != nullptr; }
+
+int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64_t lda, const float* Bmat, int64_t b_rows,
+                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  GPP_TRY(make_map_2d(&tmA, Amat, a_rows, a_cols, lda, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
+  GPP_TRY(make_map_2d(&tmB, Bmat, b_rows, b_cols, ldb, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  RowsParams p{};
+  p.mode = 1; p.out = out; p.ldo = ldo; p.alpha_host = g.alpha;
+  p.batches = g.batches; p.n_last = g.n_last;
+  p.a_row0 = g.a_row0; p.a_row_step = g.a_row_step; p.a_k0 = g.a_k0; p.a_k_step = g.a_k_step;
+  p.b_k0 = g.b_k0; p.b_k_step = g.b_k_step; p.b_col0 = g.b_col0; p.b_col_step = g.b_col_step;
+  p.tri_a = g.tri_a; p.tri_b = g.tri_b; p.out_step = g.out_step;
+  return launch_rows_maps(tmA, tmA, tmB, g.n, g.K, 0, g.ncols, p, st);
 }
 
 // out = alpha (X - A M); with nll != nullptr also the NLL epilogue (quad partials -> xb_finalize).
@@ -738,7 +804,7 @@ int launch_tc_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, con
   build_bstk_kernel<<<1024, 256, 0, st>>>(Binv, W, ldw, scal, Q, L, L_true, Bstk);
   GPP_LAUNCH_CHECK();
   RowsParams p{};
-  p.mode = 1; p.out = Vb; p.ldo = ldvb;
+  p.mode = 1; p.out = Vb; p.ldo = ldvb; p.alpha_host = 1.f;
   return launch_rows(V, ldv, Q, Xb, ldxb, L, Bstk, Q, n, Q, p, st);
 }
 

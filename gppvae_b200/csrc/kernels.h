@@ -36,9 +36,21 @@ int launch_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const 
 
 // ---- gemm_tc.cu (tcgen05 / TMA / TMEM) ----
 bool tc_pass1_supported(int64_t n, int Q, int L);
-size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L);
-int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* GC,
-                    int64_t ldgc, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g);
+int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* G,
+                    int64_t ldg, float* C, int64_t ldc, const double* scal_c, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
+
+// batched block GEMM on the tensor cores (see gemm_tc.cu)
+struct TcBlockGemm {
+  int n, n_last, K, ncols, batches;
+  int a_row0, a_row_step, a_k0, a_k_step, b_k0, b_k_step, b_col0, b_col_step, tri_a, tri_b;
+  int64_t out_step;
+  float alpha;
+};
+bool tc_blockgemm_supported(int n, int K, int ncols);
+int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64_t lda, const float* Bmat, int64_t b_rows,
+                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g, cudaStream_t st);
 
 bool tc_rows_supported(int64_t n, int K, int ncols);
 size_t tc_xb_workspace_bytes(int64_t n, int L);

@@ -484,6 +484,10 @@ static FactorLayout factor_layout(int Q) {
   f.off_part = o; o += align_up((size_t)kSumsqBlocks * sizeof(double), 256);
   f.off_tn = o;
   f.tn_bytes = tn_workspace_bytes(Q, Q, Q, 0, 1);
+  if (tc_pass1_supported(Q, Q, 0)) {
+    const size_t tcb = tc_pass1_workspace_bytes(Q, Q, 0, false);
+    if (tcb > f.tn_bytes) f.tn_bytes = tcb;
+  }
   o += align_up(f.tn_bytes, 256);
   f.total = o;
   return f;
@@ -501,6 +505,10 @@ static SolveLayout solve_layout(int Q, int L) {
   f.off_part = o; o += align_up((size_t)kSumsqBlocks * sizeof(double), 256);
   f.off_tn = o;
   f.tn_bytes = tn_workspace_bytes(Q, Q, 0, L, 0);
+  if (tc_pass1_supported(Q, Q, L)) {
+    const size_t tcb = tc_pass1_workspace_bytes(Q, Q, L, true);
+    if (tcb > f.tn_bytes) f.tn_bytes = tcb;
+  }
   o += align_up(f.tn_bytes, 256);
   f.total = o;
   return f;
@@ -561,6 +569,22 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
     int m_last = Qp - (2 * (npairs - 1) * b + b);  // rows of the last pair's D block
     if (m_last > b) m_last = b;                    // (a trailing unpaired block waits for the next level)
     const int64_t pair_stride = (int64_t)2 * b * (Qp + 1);
+    if (tc_blockgemm_supported(b, b, b)) {
+      // large levels on the tensor cores (3xTF32): T = C . Ai, then X = -Di . T
+      TcBlockGemm g{};
+      g.n = b; g.n_last = m_last; g.K = b; g.ncols = b; g.batches = npairs; g.out_step = pair_stride;
+      g.a_row0 = b; g.a_row_step = 2 * b; g.a_k0 = 0; g.a_k_step = 2 * b;       // C block of Lc: rows p0 + b, cols p0
+      g.b_k0 = 0; g.b_k_step = 2 * b; g.b_col0 = 0; g.b_col_step = 2 * b;       // Ai: rows p0, cols p0
+      g.tri_b = 1; g.alpha = 1.f;
+      GPP_TRY(launch_tc_blockgemm(Bm, Qp, Qp, Qp, Linv, Qp, Qp, Qp, Tm + (int64_t)b * Qp, Qp, g, st));
+      TcBlockGemm x{};
+      x.n = b; x.n_last = m_last; x.K = b; x.ncols = b; x.batches = npairs; x.out_step = pair_stride;
+      x.a_row0 = b; x.a_row_step = 2 * b; x.a_k0 = b; x.a_k_step = 2 * b;       // Di: rows p0 + b, cols p0 + b
+      x.b_k0 = b; x.b_k_step = 2 * b; x.b_col0 = 0; x.b_col_step = 2 * b;       // T: rows p0 + b, cols p0
+      x.tri_a = 1; x.alpha = -1.f;
+      GPP_TRY(launch_tc_blockgemm(Linv, Qp, Qp, Qp, Tm, Qp, Qp, Qp, Linv + (int64_t)b * Qp, Qp, x, st));
+      continue;
+    }
     GemmParams t{};
     t.A = Bm + (int64_t)b * Qp;  t.lda = Qp; t.strideA = pair_stride;      // C block of Lc
     t.B = Linv;                  t.ldb = Qp; t.strideB = pair_stride;      // Ai, read as B(n,k) = Ai[k][n]
@@ -580,7 +604,10 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
       set_error("factor: GPP_WANT_BINV set but Binv is null");
       return GPP_ERR_INVALID_ARGUMENT;
     }
-    GPP_TRY(launch_tn(Linv, Qp, Q, Linv, Qp, Q, nullptr, 0, 0, Q, 1, Binv, Q, nullptr, 0, nullptr, tnws, f.tn_bytes, st));
+    if (tc_pass1_supported(Q, Q, 0))
+      GPP_TRY(launch_tc_pass1(Linv, Qp, nullptr, 0, Q, Q, 0, Binv, Q, nullptr, 0, nullptr, tnws, f.tn_bytes, st));
+    else
+      GPP_TRY(launch_tn(Linv, Qp, Q, Linv, Qp, Q, nullptr, 0, 0, Q, 1, Binv, Q, nullptr, 0, nullptr, tnws, f.tn_bytes, st));
   }
   sumsq_partial_kernel<<<kSumsqBlocks, 256, 0, st>>>(Linv, Qp, Q, Q, part);
   GPP_LAUNCH_CHECK();
@@ -609,11 +636,19 @@ int launch_solve_w(const float* C, int64_t ldc, int Q, int L, int L_true, int64_
   double* part = reinterpret_cast<double*>(base + sl.off_part);
   void* tnws = base + sl.off_tn;
   const int Qp = f.Qp;
-  GemmParams g{};
-  g.A = Linv; g.lda = Qp; g.B = C; g.ldb = ldc; g.C = T1; g.ldc = L;
-  g.M = Q; g.N = L; g.K = Q; g.M_last = -1; g.alpha = 1.f; g.beta = 0.f; g.tri_a = 1;
-  GPP_TRY(launch_gemm(g, false, true, 1, st));  // T1 = Linv . C
-  GPP_TRY(launch_tn(Linv, Qp, Q, nullptr, 0, 0, T1, L, L, Q, 0, nullptr, 0, W, ldw, scal, tnws, sl.tn_bytes, st));
+  if (tc_blockgemm_supported(Q, Q, L) && tc_pass1_supported(Q, Q, L)) {
+    // tensor cores (3xTF32): T1 = Linv . C as a row GEMM, W = (v0/vn) Linv^T T1 as a transposed-A GEMM
+    TcBlockGemm g{};
+    g.n = Q; g.n_last = Q; g.K = Q; g.ncols = L; g.batches = 1; g.tri_a = 1; g.alpha = 1.f;
+    GPP_TRY(launch_tc_blockgemm(Linv, Q, Q, Qp, C, Q, L, ldc, T1, L, g, st));
+    GPP_TRY(launch_tc_pass1(Linv, Qp, T1, L, Q, Q, L, nullptr, 0, W, ldw, scal, tnws, sl.tn_bytes, st));
+  } else {
+    GemmParams g{};
+    g.A = Linv; g.lda = Qp; g.B = C; g.ldb = ldc; g.C = T1; g.ldc = L;
+    g.M = Q; g.N = L; g.K = Q; g.M_last = -1; g.alpha = 1.f; g.beta = 0.f; g.tri_a = 1;
+    GPP_TRY(launch_gemm(g, false, true, 1, st));  // T1 = Linv . C
+    GPP_TRY(launch_tn(Linv, Qp, Q, nullptr, 0, 0, T1, L, L, Q, 0, nullptr, 0, W, ldw, scal, tnws, sl.tn_bytes, st));
+  }
   sumsq_partial_kernel<<<kSumsqBlocks, 256, 0, st>>>(W, ldw, Q, L, part);
   GPP_LAUNCH_CHECK();
   solve_scalars_kernel<<<1, 256, 0, st>>>(L_true, n_total, part, kSumsqBlocks, scal);
