@@ -207,6 +207,16 @@ __device__ __forceinline__ void invert64(const Block64& As, Block64& Xs, float (
 //       i.e. the trailing update of the PREVIOUS panel, which is off the critical path of this step.
 // Column block c thus receives panel k < c - 1 from the wide CTAs of step k + 1 and panel c - 1 from its own panel
 // CTAs; both roles only read what earlier launches finished (column j-1) and write disjoint blocks.
+#ifdef GPP_CHOL_PROF
+__device__ long long g_chol_prof[64][8];
+#define CPROF(slot) do { if (threadIdx.x == 0 && blockIdx.x == (npanel > 1 ? 1 : 0)) g_chol_prof[j][slot] = clock64(); } while (0)
+extern "C" int gpp_debug_chol_prof(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_chol_prof, sizeof(g_chol_prof)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define CPROF(slot) do { } while (0)
+#endif
+
 struct StepSmem {
   Block64 As, Xs, LsT, PsT;   // diagonal block, this CTA's block row, L[j, j-1]^T, L[j+b, j-1]^T
   float rd16[SB];
@@ -257,24 +267,46 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
     return;
   }
   // -------------------------------------------------------------- panel role
+  CPROF(0);
   StepSmem& S = *reinterpret_cast<StepSmem*>(step_smem);
   const int b = (int)blockIdx.x;
   const float* D = Bm + (int64_t)k0 * (Qp + 1);
   float* P = Bm + (int64_t)(k0 + b * NB) * Qp + k0;   // block (j + b, j); unused for b == 0
-  for (int e = tid; e < NB * NB; e += kPotfThreads) S.As.a[e >> 6][e & 63] = D[(int64_t)(e >> 6) * Qp + (e & 63)];
-  for (int e = tid; e < (NB / SB) * SB * (SB + 1); e += kPotfThreads) (&S.li16[0][0][0])[e] = 0.f;
-  if (b > 0)
-    for (int e = tid; e < NB * NB; e += kPotfThreads) S.Xs.a[e >> 6][e & 63] = P[(int64_t)(e >> 6) * Qp + (e & 63)];
-  if (j > 0) {
-    // rank-64 update from panel j - 1:  D -= Lj Lj^T,  P -= Lp Lj^T   (operands staged transposed: [k][row])
+  // all global loads of this CTA (up to four 64 x 64 blocks) are issued before the first shared-memory store, as
+  // 128-bit loads: one L2 round trip instead of sixteen
+  {
+    const int lr = tid >> 4, lc = (tid & 15) * 4;   // 16 rows x 16 float4 per pass, 4 passes per block
     const float* Lj = D - NB;
     const float* Lp = P - NB;
-    for (int e = tid; e < NB * NB; e += kPotfThreads) {
-      const int r = e >> 6, c = e & 63;
-      S.LsT.a[c][r] = Lj[(int64_t)r * Qp + c];
-      if (b > 0) S.PsT.a[c][r] = Lp[(int64_t)r * Qp + c];
+    float4 vd[4], vp[4], vl[4], vq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t off = (int64_t)(lr + 16 * i) * Qp + lc;
+      vd[i] = *reinterpret_cast<const float4*>(D + off);
+      if (b > 0) vp[i] = *reinterpret_cast<const float4*>(P + off);
+      if (j > 0) {
+        vl[i] = *reinterpret_cast<const float4*>(Lj + off);
+        if (b > 0) vq[i] = *reinterpret_cast<const float4*>(Lp + off);
+      }
     }
+    for (int e = tid; e < (NB / SB) * SB * (SB + 1); e += kPotfThreads) (&S.li16[0][0][0])[e] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = lr + 16 * i;
+      *reinterpret_cast<float4*>(&S.As.a[r][lc]) = vd[i];
+      if (b > 0) *reinterpret_cast<float4*>(&S.Xs.a[r][lc]) = vp[i];
+      if (j > 0) {   // rank-64 update operands staged transposed: [k][row]
+        S.LsT.a[lc + 0][r] = vl[i].x; S.LsT.a[lc + 1][r] = vl[i].y; S.LsT.a[lc + 2][r] = vl[i].z; S.LsT.a[lc + 3][r] = vl[i].w;
+        if (b > 0) {
+          S.PsT.a[lc + 0][r] = vq[i].x; S.PsT.a[lc + 1][r] = vq[i].y; S.PsT.a[lc + 2][r] = vq[i].z; S.PsT.a[lc + 3][r] = vq[i].w;
+        }
+      }
+    }
+  }
+  if (j > 0) {
+    // rank-64 update from panel j - 1:  D -= Lj Lj^T,  P -= Lp Lj^T
     __syncthreads();
+    CPROF(1);
     const int ty = tid >> 4, tx = tid & 15;
     float ad[4][4], ap[4][4];
 #pragma unroll
@@ -317,7 +349,9 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
       }
   }
   __syncthreads();
+  CPROF(2);
   factor64(S.As, S.rd16, S.li16);
+  CPROF(3);
   if (b == 0) {
     float* dst = Ld + (size_t)j * NB * NB;
     for (int e = tid; e < NB * NB; e += kPotfThreads) dst[e] = S.As.a[e >> 6][e & 63];
@@ -332,10 +366,14 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
       float t[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) t[jj] = S.Xs.a[r][o + cq + jj];
-      for (int k = 0; k < o; ++k) {
-        const float xk = S.Xs.a[r][k];
+      for (int k = 0; k < o; k += 4) {
+        const float4 x4 = *reinterpret_cast<const float4*>(&S.Xs.a[r][k]);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) t[jj] = fmaf(-xk, S.As.a[o + cq + jj][k], t[jj]);
+        for (int jj = 0; jj < 4; ++jj) {
+          const float4 l4 = *reinterpret_cast<const float4*>(&S.As.a[o + cq + jj][k]);
+          t[jj] = fmaf(-x4.x, l4.x, t[jj]); t[jj] = fmaf(-x4.y, l4.y, t[jj]);
+          t[jj] = fmaf(-x4.z, l4.z, t[jj]); t[jj] = fmaf(-x4.w, l4.w, t[jj]);
+        }
       }
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) S.Xs.a[r][o + cq + jj] = t[jj];
@@ -355,7 +393,9 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
     }
   }
   __syncthreads();
+  CPROF(4);
   for (int e = tid; e < NB * NB; e += kPotfThreads) P[(int64_t)(e >> 6) * Qp + (e & 63)] = S.Xs.a[e >> 6][e & 63];
+  CPROF(5);
 }
 
 // Linv diagonal blocks: one CTA per 64 x 64 diagonal factor (Ld[j]) -> Linv[j*64.., j*64..] (ld = ldd).
