@@ -27,8 +27,8 @@
 //
 // Warp roles per CTA (512 threads, setmaxnreg re-balanced): warp 0 TMA producer (own halves), warp 1 MMA issuer
 // (leader CTA only) + TMEM owner, warps 4-7 converters, warps 8-15 drain / epilogue of the CTA's own 128 rows.
-// Barriers: full[s] (local TMA -> local converters), conv[s] (converters of BOTH CTAs -> leader), empty[s] and
-// tfull[b] (MMA commit, multicast to both CTAs), tempty[b] (drain warps of both CTAs -> leader).
+// Barriers: full[s] (local TMA -> local converters), conv[s] (converters of BOTH CTAs -> leader), empty[s], lo_empty[s]
+// and tfull[b] (MMA commit, multicast to both CTAs), tempty[b] (drain warps of both CTAs -> leader).
 // Pass 1 is persistent over (tile, k-split) units with a deterministic split-K: every unit writes its own partial
 // tile, tc_reduce_kernel sums them in a fixed order (fp64) and tc_mirror_kernel fills the upper triangle of G.
 #include "common.cuh"
@@ -44,20 +44,25 @@ namespace {
 #ifndef GPP_TC_WIN
 #define GPP_TC_WIN 4
 #endif
-#ifndef GPP_TC_STAGES
-#define GPP_TC_STAGES 6
+#ifndef GPP_TC_RAW
+#define GPP_TC_RAW 9     // raw (fp32 = hi) tiles in flight: TMA -> converter -> MMA
+#endif
+#ifndef GPP_TC_LO
+#define GPP_TC_LO 4      // lo planes in flight: converter -> MMA
 #endif
 constexpr int TM = 256, TN = 256;   // tile of a CTA pair
 constexpr int HM = 128, HN = 128;   // what one CTA stages of it
 #ifndef GPP_TC_GROUP
 #define GPP_TC_GROUP 2
 #endif
-constexpr int TBK = 16, kStages = GPP_TC_STAGES, kWin = GPP_TC_WIN, kGroup = GPP_TC_GROUP;
+constexpr int TBK = 16, kRaw = GPP_TC_RAW, kLo = GPP_TC_LO, kWin = GPP_TC_WIN, kGroup = GPP_TC_GROUP;
 constexpr int kABytes = HM * TBK * 4, kBBytes = HN * TBK * 4, kRawBytes = kABytes + kBBytes;   // 8 K + 8 K
-constexpr int kStageBytes = 2 * kRawBytes;                                                      // raw (= hi) + lo
+// Two rings: a raw tile is occupied from the TMA issue until its last MMA (TMA latency + conversion + MMA), its lo
+// plane only from the conversion on, so the lo ring can be much shorter than the raw ring and the shared memory
+// goes into TMA prefetch depth instead.
 constexpr int kTcThreads = 512;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-static_assert(kGroup >= 1 && kGroup <= kWin && kGroup < kStages, "a group must fit in the stage ring with room to prefetch");
+constexpr int kSmemBytes = (kRaw + kLo) * kRawBytes + 1024 /*align*/ + 512 /*barriers*/;
+static_assert(kGroup >= 1 && kGroup <= kWin && kGroup < kLo && kLo <= kRaw, "a group must fit in the lo ring with room to convert ahead");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // Optional role profiling (-DGPP_TC_PROF): cycles each role spends waiting on its barriers, per CTA.
@@ -74,7 +79,7 @@ __device__ unsigned long long g_prof[512][16];
 #endif
 
 struct TcShared {
-  uint64_t full[kStages], conv[kStages], empty[kStages], tfull[2], tempty[2];
+  uint64_t full[kRaw], empty[kRaw], conv[kLo], lo_empty[kLo], tfull[2], tempty[2];
   uint32_t tmem_base;
 };
 
@@ -115,12 +120,15 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 
 // ---- pieces shared by the two kernels ----------------------------------------------------------------------
 __device__ __forceinline__ TcShared* tc_prologue(uint8_t* base, uint32_t& tmem) {
-  TcShared* sm = reinterpret_cast<TcShared*>(base + kStages * kStageBytes);
+  TcShared* sm = reinterpret_cast<TcShared*>(base + (kRaw + kLo) * kRawBytes);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kRaw; ++s) {
       mbar_init(&sm->full[s], 1);
-      mbar_init(&sm->conv[s], 8);     // 4 converter warps x 2 CTAs (used in the leader)
       mbar_init(&sm->empty[s], 1);
+    }
+    for (int s = 0; s < kLo; ++s) {
+      mbar_init(&sm->conv[s], 8);     // 4 converter warps x 2 CTAs (used in the leader)
+      mbar_init(&sm->lo_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm->tfull[b], 1);
@@ -144,25 +152,31 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
 
 // converter warps: wait for the raw tile of stage s, write the lo plane, tell the leader
 __device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint32_t conv0_leader, uint32_t it,
-                                              unsigned long long& pw0) {
+                                              unsigned long long& pw0, unsigned long long& pw1) {
   const int t = threadIdx.x - 128, lane = threadIdx.x & 31;
-  const int s = it % kStages;
-  PROF_WAIT(pw0, mbar_wait(&sm->full[s], (it / kStages) & 1));
-  const float4* raw = reinterpret_cast<const float4*>(base + s * kStageBytes);
-  float4* lo = reinterpret_cast<float4*>(base + s * kStageBytes + kRawBytes);
+  const int s = it % kRaw, sl = it % kLo;
+  PROF_WAIT(pw0, mbar_wait(&sm->full[s], (it / kRaw) & 1));
+  PROF_WAIT(pw1, mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1));
+  // explicit shared-space accesses, all loads before the first store: through generic pointers the compiler emitted
+  // LD.E / ST.E and kept every load behind the previous store (possible aliasing), i.e. eight exposed shared-memory
+  // latencies per stage, which made these warps the bottleneck of the whole pipeline
+  const uint32_t raw = smem_u32(base + s * kRawBytes) + t * 16, lo = smem_u32(base + (kRaw + sl) * kRawBytes) + t * 16;
+  constexpr int kIters = kRawBytes / 16 / 128;
+  float4 v[kIters];
 #pragma unroll
-  for (int i = 0; i < kRawBytes / 16 / 128; ++i) {
-    const float4 v = raw[t + i * 128];
-    float4 l;
-    l.x = tf32_rn(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
-    l.y = tf32_rn(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
-    l.z = tf32_rn(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
-    l.w = tf32_rn(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-    lo[t + i * 128] = l;
+  for (int i = 0; i < kIters; ++i)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                 : "r"(raw + i * 2048));
+#pragma unroll
+  for (int i = 0; i < kIters; ++i) {
+    const float4 l = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + i * 2048), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
+                 : "memory");
   }
   fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
   __syncwarp();
-  if (lane == 0) mbar_arrive_cluster(conv0_leader + 8u * s);
+  if (lane == 0) mbar_arrive_cluster(conv0_leader + 8u * sl);
 }
 
 // MMA issuer (one thread of the leader): one window of `wst` stages starting at ring position `it` into TMEM buffer d.
@@ -176,12 +190,12 @@ __device__ __forceinline__ void issue_window(uint8_t* base, TcShared* sm, uint32
   uint32_t acc = 0;
   for (int g0 = 0; g0 < wst; g0 += kGroup) {
     const int g1 = min(wst, g0 + kGroup);
-    PROF_WAIT(pw1, for (int j = g0; j < g1; ++j)
-                       mbar_wait_cluster(&sm->conv[(it + j) % kStages], ((it + j) / kStages) & 1));
-    tcgen05_fence_after();
     for (int j = g0; j < g1; ++j) {
-      const uint32_t a_hi = smem_u32(base + ((it + j) % kStages) * kStageBytes), b_hi = a_hi + kABytes;
-      const uint32_t a_lo = a_hi + kRawBytes, b_lo = a_lo + kABytes;
+      // each stage's cross terms go out as soon as that stage is converted (the pipe has work while the next converts)
+      PROF_WAIT(pw1, mbar_wait_cluster(&sm->conv[(it + j) % kLo], ((it + j) / kLo) & 1));
+      tcgen05_fence_after();
+      const uint32_t a_hi = smem_u32(base + ((it + j) % kRaw) * kRawBytes), b_hi = a_hi + kABytes;
+      const uint32_t a_lo = smem_u32(base + (kRaw + (it + j) % kLo) * kRawBytes), b_lo = a_lo + kABytes;
 #pragma unroll
       for (int kk = 0; kk < TBK / 8; ++kk) {
         const uint64_t dah = A_MN ? umma_desc(a_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32)
@@ -196,8 +210,8 @@ __device__ __forceinline__ void issue_window(uint8_t* base, TcShared* sm, uint32
       }
     }
     for (int j = g0; j < g1; ++j) {
-      const int s = (it + j) % kStages;
-      const uint32_t a_hi = smem_u32(base + s * kStageBytes), b_hi = a_hi + kABytes;
+      const int s = (it + j) % kRaw;
+      const uint32_t a_hi = smem_u32(base + s * kRawBytes), b_hi = a_hi + kABytes;
 #pragma unroll
       for (int kk = 0; kk < TBK / 8; ++kk) {
         const uint64_t dah = A_MN ? umma_desc(a_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32)
@@ -205,7 +219,8 @@ __device__ __forceinline__ void issue_window(uint8_t* base, TcShared* sm, uint32
         const uint64_t dbh = umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
         umma_tf32_pair(d, dah, dbh, idesc, 1);
       }
-      umma_commit_pair(&sm->empty[s], 3);
+      umma_commit_pair(&sm->empty[s], 3);                      // raw tile and lo plane free in both CTAs
+      umma_commit_pair(&sm->lo_empty[(it + j) % kLo], 3);
     }
   }
 }
@@ -262,9 +277,9 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
         const CUtensorMap* mb = is_c ? &tmX : &tmV;
         const int acol = tm * TM + (int)rank * HM, bcol = tn * TN + (int)rank * HN;
         for (int st = 0; st < nst; ++st, ++it) {
-          const int s = it % kStages;
-          PROF_WAIT(pw0, mbar_wait(&sm->empty[s], ((it / kStages) & 1) ^ 1));
-          uint8_t* dst = base + s * kStageBytes;
+          const int s = it % kRaw;
+          PROF_WAIT(pw0, mbar_wait(&sm->empty[s], ((it / kRaw) & 1) ^ 1));
+          uint8_t* dst = base + s * kRawBytes;
           const int row = (int)(r0 + (int64_t)st * TBK);
           mbar_arrive_expect_tx(&sm->full[s], kRawBytes);
 #pragma unroll
@@ -306,7 +321,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       const int64_t r0 = (int64_t)split * p.rows_per_split;
       const int64_t r1 = min(p.n, r0 + p.rows_per_split);
       const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
-      for (int st = 0; st < nst; ++st, ++it) convert_stage(base, sm, conv0, it, pw0);
+      for (int st = 0; st < nst; ++st, ++it) convert_stage(base, sm, conv0, it, pw0, pw1);
     }
     if (threadIdx.x == 128) PROF_STORE(2);
   } else {
@@ -450,9 +465,9 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int bcol = p.b_col0 + un.batch * p.b_col_step + un.ct * TN + (int)rank * HN;
         const int ak0 = p.a_k0 + un.batch * p.a_k_step, bk0 = p.b_k0 + un.batch * p.b_k_step;
         for (int st = un.k_begin; st < un.k_end; ++st, ++it) {
-          const int s = it % kStages;
-          PROF_WAIT(pw0, mbar_wait(&sm->empty[s], ((it / kStages) & 1) ^ 1));
-          uint8_t* dst = base + s * kStageBytes;
+          const int s = it % kRaw;
+          PROF_WAIT(pw0, mbar_wait(&sm->empty[s], ((it / kRaw) & 1) ^ 1));
+          uint8_t* dst = base + s * kRawBytes;
           mbar_arrive_expect_tx(&sm->full[s], kRawBytes);
           int kb;   // row of B where this k-block starts
           if (st < nst1) {
@@ -489,7 +504,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     uint32_t it = 0;
     for (int64_t u = pair; u < nunits; u += npairs) {
       const RowsUnit un = rows_unit(p, u, nst);
-      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_stage(base, sm, conv0, it, pw0);
+      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_stage(base, sm, conv0, it, pw0, pw1);
     }
   } else {
     setmaxnreg_inc<184>();

@@ -209,6 +209,13 @@ __device__ __forceinline__ float tf32_rn(float a) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
   return __uint_as_float(r);
 }
+// lo plane when the raw fp32 value itself is the hi operand (kind::tf32 truncates it in hardware):
+// lo = rn_tf32(a - trunc_tf32(a)); the difference is exact in fp32 and far from overflow, so the rounding is a plain
+// add-half-ulp-and-mask (ties away from zero, like cvt.rna) without cvt's special-value handling.
+__device__ __forceinline__ float tf32_lo(float a) {
+  const float d = a - __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  return __uint_as_float((__float_as_uint(d) + 0x1000u) & 0xFFFFE000u);
+}
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
   hi = tf32_rn(a);
   lo = tf32_rn(a - hi);
