@@ -321,6 +321,12 @@ def run_ours(args):
     flops_total = float(n) * (Q * (Q + 1) + 4.0 * Q * L + Q + 3 * L)
     bytes_total = float(n) * (12 * Q + 12 * L + 20)
     t_roof = max(flops_total / (tf32_peak * 1e12), bytes_total / (pk["hbm_gbs"] * 1e9)) * 1e3
+    # executed tensor work: every product is issued as 3 TF32 MMAs (hi.hi + hi.lo + lo.hi)
+    flops_gemm = float(n) * (Q * (Q + 1) + 4.0 * Q * L)
+    t_roof_k3 = max(3.0 * flops_gemm / (tf32_peak * 1e12), bytes_total / (pk["hbm_gbs"] * 1e9)) * 1e3
+    # DRAM traffic of the pass-1 kernel per launch from the committed `ncu --set full` captures (profiles/):
+    # dram__bytes_read.sum + dram__bytes_write.sum at 1 GPU; None where no capture exists for the shape
+    traffic = {("c3", 1): 79.229183e9 + 0.450472e9, ("c2", 1): 562.076928e6 + 66.275840e6}.get((args.workload, world))
     line = {
         "metric": METRIC, "value": N / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -330,12 +336,18 @@ def run_ours(args):
                 "ms_per_step": ms_e2e, "api": "Vmodel.forward + GP.taylor_coeff(need_vb=False) from pinned host "
                                               "tensors; nll, Xb, vbs copied back to pinned host memory",
                 "c_entry_ms_per_step": ms_c},
-        "roofline": {"bound": "tensor", "kernel": "pass 1: V^T[V|Z] (tn_partial_kernel + tn_reduce_kernel)",
+        "roofline": {"bound": "tensor", "kernel": "pass 1: V^T[V|Z] (tc_pass1_kernel + tc_reduce_kernel + tc_mirror_kernel)",
                      "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": (achieved / tf32_peak) if achieved else None, "traffic": None,
+                     "frac": (achieved / tf32_peak) if achieved else None, "traffic": traffic,
+                     "traffic_source": "ncu --set full, profiles/r01_pass1_c3_pair_ncu_full.txt / "
+                                       "r01_tc_pair_kernels_c2_ncu_full.txt" if traffic else None,
+                     "algorithmic_bytes_per_launch": float(n) * (4 * Q + 4 * L) + 4.0 * Q * (Q + L),
                      "peak_source": f"{pk['source']} bf16_tflops_sustained / 2 (dense TF32), k=1 algorithmic flops",
                      "algorithmic_flops_per_launch": flops_pass1, "ms_per_launch": t_pass1,
-                     "whole_step_frac_of_roofline": t_roof / ms, "whole_step_roofline_ms": t_roof},
+                     "tf32_passes": 3, "executed_tflops": 3.0 * achieved if achieved else None,
+                     "executed_frac": (3.0 * achieved / tf32_peak) if achieved else None,
+                     "whole_step_frac_of_roofline": t_roof / ms, "whole_step_roofline_ms": t_roof,
+                     "whole_step_frac_of_roofline_at_3_passes": t_roof_k3 / ms, "whole_step_roofline_ms_at_3_passes": t_roof_k3},
         "stage_ms": stage_ms, "nll_mean": nll_mean, "xb_sumsq": xb_sq, "vbs": vbs_host,
         "full_taylor_coeff": None if ms_full is None else {"ms_per_step": ms_full, "value": N / (ms_full * 1e-3)},
     }

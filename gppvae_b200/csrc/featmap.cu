@@ -90,20 +90,33 @@ khatri_rao_fwd_kernel(const float* __restrict__ xn, int64_t P, int p, const floa
     }
     __syncwarp();
     float4* vrow = reinterpret_cast<float4*>(V + r * ldv);
-    for (int c4 = lane; c4 < Q4; c4 += 32) {
-      const int c = c4 << 2;
-      int j = c / q;
-      int k = c - j * q;
-      float o[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        o[e] = ok ? xs[j] * ws[k] : qnan;
-        if (++k == q) {
-          k = 0;
-          ++j;
-        }
+    const int q4 = q >> 2;
+    if ((q & 3) == 0 && (p & 3) == 0 && q4 <= 32 && (32 % q4) == 0) {
+      // fast path (q = 4, 8, 16, ..., 128): a lane's four columns share one j and its view quad never changes, so a
+      // float4 of the row is one shared-memory read of x, four multiplies and one 128-bit store
+      const int kq = lane % q4, jstep = 32 / q4;
+      const float4 w4 = ok ? *reinterpret_cast<const float4*>(ws + 4 * kq) : make_float4(qnan, qnan, qnan, qnan);
+      int j = lane / q4;
+      for (int c4 = lane; c4 < Q4; c4 += 32, j += jstep) {
+        const float x = ok ? xs[j] : qnan;
+        vrow[c4] = make_float4(x * w4.x, x * w4.y, x * w4.z, x * w4.w);
       }
-      vrow[c4] = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      for (int c4 = lane; c4 < Q4; c4 += 32) {
+        const int c = c4 << 2;
+        int j = c / q;
+        int k = c - j * q;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          o[e] = ok ? xs[j] * ws[k] : qnan;
+          if (++k == q) {
+            k = 0;
+            ++j;
+          }
+        }
+        vrow[c4] = make_float4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }

@@ -351,43 +351,64 @@ __global__ void __launch_bounds__(kGemmThreads, 2) xb_kernel(XbParams p) {
   }
 }
 
-// nll_i = 0.5 * sum_t quad_part[t][i] + ROWCONST ; scal[XB2], scal[QUAD] by a fixed-order reduction.
-__global__ void __launch_bounds__(1024) xb_finalize_kernel(const float* __restrict__ quad_part, int tiles_n, int64_t n,
-                                                           const double* __restrict__ xb2_part, int64_t nparts,
-                                                           double* __restrict__ scal, float* __restrict__ nll) {
-  __shared__ double red[32];
+// nll_i = 0.5 * sum_t quad_part[t][i] + ROWCONST ; scal[XB2], scal[QUAD] by a fixed-order (deterministic) two-level
+// reduction: kXbFinalizeBlocks CTAs each own a contiguous range of rows / partials and leave one double each, a
+// single CTA adds those in index order.
+__global__ void __launch_bounds__(256) xb_finalize_rows_kernel(const float* __restrict__ quad_part, int tiles_n,
+                                                               int64_t n, const double* __restrict__ xb2_part,
+                                                               int64_t nparts, const double* __restrict__ scal,
+                                                               float* __restrict__ nll, double* __restrict__ fin) {
+  __shared__ double red[2][8];
   const double rowconst = scal[GPP_S_ROWCONST];
+  const int64_t rows_per = (n + gridDim.x - 1) / gridDim.x, parts_per = (nparts + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per, r1 = min(n, r0 + rows_per);
+  const int64_t p0 = (int64_t)blockIdx.x * parts_per, p1 = min(nparts, p0 + parts_per);
   double qsum = 0, xsum = 0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
     float q = 0.f;
     for (int t = 0; t < tiles_n; ++t) q += quad_part[(int64_t)t * n + i];
     nll[i] = (float)(0.5 * (double)q + rowconst);
     qsum += (double)q;
   }
-  for (int64_t i = threadIdx.x; i < nparts; i += blockDim.x) xsum += xb2_part[i];
-  for (int pass = 0; pass < 2; ++pass) {
-    double v = warp_sum(pass == 0 ? qsum : xsum);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-      scal[pass == 0 ? GPP_S_QUAD : GPP_S_XB2] = s;
-    }
-    __syncthreads();
+  for (int64_t i = p0 + threadIdx.x; i < p1; i += blockDim.x) xsum += xb2_part[i];
+  qsum = warp_sum(qsum);
+  xsum = warp_sum(xsum);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = qsum;
+    red[1][threadIdx.x >> 5] = xsum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+    fin[2 * blockIdx.x + 0] = a;
+    fin[2 * blockIdx.x + 1] = b;
   }
 }
 
+__global__ void xb_finalize_sum_kernel(const double* __restrict__ fin, int nblocks, double* __restrict__ scal) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int i = 0; i < nblocks; ++i) { a += fin[2 * i]; b += fin[2 * i + 1]; }
+    scal[GPP_S_QUAD] = a;
+    scal[GPP_S_XB2] = b;
+  }
+}
+
+// `fin` = kXbFinalizeBlocks * 2 doubles of workspace (xb_finalize_bytes()).
 int launch_xb_finalize(const float* quad_part, int tiles_n, int64_t n, const double* xb2_part, int64_t nparts,
-                       double* scal, float* nll, cudaStream_t st) {
-  xb_finalize_kernel<<<1, 1024, 0, st>>>(quad_part, tiles_n, n, xb2_part, nparts, scal, nll);
+                       double* fin, double* scal, float* nll, cudaStream_t st) {
+  xb_finalize_rows_kernel<<<kXbFinalizeBlocks, 256, 0, st>>>(quad_part, tiles_n, n, xb2_part, nparts, scal, nll, fin);
+  GPP_LAUNCH_CHECK();
+  xb_finalize_sum_kernel<<<1, 32, 0, st>>>(fin, kXbFinalizeBlocks, scal);
   GPP_LAUNCH_CHECK();
   return GPP_OK;
 }
 
 size_t xb_workspace_bytes(int64_t n, int L) {
   const int64_t tiles_n = ceil_div(L, BN), tiles_m = ceil_div(n, BM);
-  return align_up((size_t)tiles_n * n * sizeof(float), 256) + (size_t)tiles_m * tiles_n * sizeof(double);
+  return align_up((size_t)tiles_n * n * sizeof(float), 256) + align_up((size_t)tiles_m * tiles_n * sizeof(double), 256) +
+         xb_finalize_bytes();
 }
 
 int launch_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n, int Q,
@@ -418,8 +439,8 @@ int launch_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const fl
   xb_kernel<<<(unsigned)(tiles_m * tiles_n), kGemmThreads, 0, st>>>(p);
   GPP_LAUNCH_CHECK();
   if (nll) {
-    xb_finalize_kernel<<<1, 1024, 0, st>>>(p.quad_part, (int)tiles_n, n, p.xb2_part, tiles_m * tiles_n, scal, nll);
-    GPP_LAUNCH_CHECK();
+    double* fin = p.xb2_part + align_up((size_t)tiles_m * tiles_n * sizeof(double), 256) / sizeof(double);
+    GPP_TRY(launch_xb_finalize(p.quad_part, (int)tiles_n, n, p.xb2_part, tiles_m * tiles_n, fin, scal, nll, st));
   }
   return GPP_OK;
 }

@@ -735,7 +735,8 @@ bool tc_rows_supported(int64_t n, int K, int ncols) { return n >= 512 && K >= 64
 
 size_t tc_xb_workspace_bytes(int64_t n, int L) {
   const int64_t col_tiles = ceil_div(L, TN), row_tiles = ceil_div(n, TM);
-  return align_up((size_t)col_tiles * 2 * n * sizeof(float), 256) + (size_t)row_tiles * col_tiles * 16 * sizeof(double);
+  return align_up((size_t)col_tiles * 2 * n * sizeof(float), 256) +
+         align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256) + xb_finalize_bytes();
 }
 
 static int launch_rows_maps(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB, int64_t n,
@@ -801,7 +802,11 @@ int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const
     p.xb2_part = reinterpret_cast<double*>(static_cast<char*>(ws) + align_up((size_t)col_tiles * 2 * n * sizeof(float), 256));
   }
   GPP_TRY(launch_rows(V, ldv, Q, nullptr, 0, 0, W, ldw, n, L, p, st));
-  if (nll) GPP_TRY(launch_xb_finalize(p.quad_part, (int)(col_tiles * 2), n, p.xb2_part, row_tiles * col_tiles * 16, scal, nll, st));
+  if (nll) {
+    double* fin = p.xb2_part + align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256) / sizeof(double);
+    GPP_TRY(launch_xb_finalize(p.quad_part, (int)(col_tiles * 2), n, p.xb2_part, row_tiles * col_tiles * 16, fin, scal,
+                               nll, st));
+  }
   return GPP_OK;
 }
 

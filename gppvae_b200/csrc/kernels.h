@@ -62,8 +62,10 @@ int launch_tc_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, con
                  int64_t ldw, const double* scal, int64_t n, int Q, int L, int L_true, float* Vb, int64_t ldvb, void* ws,
                  size_t ws_bytes, cudaStream_t st);
 // gemm_simt.cu: nll_i = 0.5 sum_t quad_part[t][i] + ROWCONST; scal[XB2], scal[QUAD]
+constexpr int kXbFinalizeBlocks = 296;
+inline size_t xb_finalize_bytes() { return (size_t)kXbFinalizeBlocks * 2 * sizeof(double); }
 int launch_xb_finalize(const float* quad_part, int tiles_n, int64_t n, const double* xb2_part, int64_t nparts,
-                       double* scal, float* nll, cudaStream_t st);
+                       double* fin, double* scal, float* nll, cudaStream_t st);
 
 // ---- qspace.cu ----
 size_t factor_workspace_bytes(int Q);

@@ -422,16 +422,29 @@ __global__ void __launch_bounds__(kPotfThreads) diag_store_kernel(const float* _
 }
 
 // ------------------------------------------------------------------ reductions
-// partials[blockIdx.x] = sum over this CTA's rows of sum_{c < cols} A[r][c]^2 (fixed order)
+// partials[blockIdx.x] = sum over this CTA's rows of sum_{c < cols} A[r][c]^2 (fixed order).  Squares are summed in
+// fp32 over 16 elements at a time and those short sums in double (B200's fp64 pipe is slow; a 16-term fp32 sum of
+// squares carries ~1e-7 relative error, far below what tr B^-1 / ||W||^2 need).  cols % 4 == 0, rows 16-byte aligned.
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ A, int64_t ld, int rows, int cols,
                                                             double* __restrict__ partials) {
   __shared__ double red[8];
   double s = 0;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x)
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-      const double v = (double)A[(int64_t)r * ld + c];
-      s += v * v;
+  const int c4n = cols >> 2;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float4* row = reinterpret_cast<const float4*>(A + (int64_t)r * ld);
+    for (int c0 = threadIdx.x; c0 < c4n; c0 += 4 * blockDim.x) {
+      float f = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * blockDim.x;
+        if (c < c4n) {
+          const float4 v = row[c];
+          f = fmaf(v.x, v.x, f); f = fmaf(v.y, v.y, f); f = fmaf(v.z, v.z, f); f = fmaf(v.w, v.w, f);
+        }
+      }
+      s += (double)f;
     }
+  }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -442,7 +455,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   }
 }
 
-constexpr int kSumsqBlocks = 256;
+constexpr int kSumsqBlocks = 592;
 
 // deterministic single-CTA sum of `nparts` doubles (+ optional 2 sum log diag(Lc))
 __device__ __forceinline__ double block_sum_256(double v, double* red) {
