@@ -71,10 +71,12 @@ def cpu_reference_timing(cfg, budget_s: float = 20.0, rows: int | None = None):
     run(min(256, N))                       # thread-pool / MKL warm-up
     tb, _ = run(min(256, N))               # ~ fixed cost b
     if rows is None:
-        # per-row cost estimate: 4 Q^2 + 4 Q L MACs ~ 2x flops; assume ~20 GFLOP/s/thread to size the sample
-        per_row = 2.0 * (4.0 * Q * Q + 4.0 * Q * L) / (20e9 * threads)
-        rows = int(max(1024, min(N, (budget_s - min(tb, budget_s * 0.5)) / max(per_row, 1e-9))))
-        rows = min(rows, 65536, N)
+        # calibrate the per-row cost on a small sample, then size the timed sample to ~budget_s of CPU work
+        r_cal = min(N, 4096)
+        tc, _ = run(r_cal)
+        per_row = max(tc - tb, 1e-6) / max(r_cal - min(256, N), 1)
+        rows = int(max(1024, min(N, (budget_s - min(tb, budget_s * 0.5)) / per_row)))
+        rows = min(rows, 262144, N)
     ts, _ = run(rows)
     a = max(ts - tb, 1e-9) / max(rows - min(256, N), 1)
     full = a * N + tb

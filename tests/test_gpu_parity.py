@@ -384,3 +384,42 @@ def test_tensor_core_pass1_against_fp64_and_simt(dev, n, Q, L):
     print(f"[pass1 n={n} Q={Q} L={L}] max-rel err: tcgen05 {e_tc:.2e}  simt {e_simt:.2e}  worst elementwise {worst:.2e}")
     assert e_tc < 1e-6 and e_simt < 1e-6
     assert torch.equal(GC[:, :Q], GC[:, :Q].t())
+
+
+@pytest.mark.parametrize("Q,L,r", [(1024, 256, 1.0), (1600, 132, 50.0), (2048, 256, 400.0)])
+def test_qspace_large_against_fp64(dev, Q, L, r):
+    """The Q-space stage at sizes where it runs on the tensor cores (block GEMMs of the triangular inverse from 512
+    rows up, T1 = Linv C, W = r Linv^T T1, Binv = Linv^T Linv), including a Q that is not a power-of-two multiple of
+    the panel (ragged last pair of the recursive doubling), against a float64 Cholesky of the same B."""
+    from gppvae_b200 import ops
+    from gppvae_b200._lib import S_LOGDETB, S_TRBINV
+    torch.manual_seed(Q)
+    n = 3 * Q
+    V = torch.randn(n, Q, device=dev, dtype=torch.float64) / Q ** 0.5
+    V[:, : Q // 8] *= 4.0                                  # a few dominant directions: cond(B) ~ 1 + 16 r n / Q
+    G64 = V.t() @ V
+    C64 = torch.randn(Q, L, device=dev, dtype=torch.float64)
+    vn = 1.0 / (1.0 + r)
+    vs = torch.tensor([1.0 - vn, vn], device=dev, dtype=torch.float32)
+    r_eff = float(vs[0].double() / vs[1].double())
+    B64 = torch.eye(Q, device=dev, dtype=torch.float64) + r_eff * G64
+    Lc = torch.linalg.cholesky(B64)
+    Binv64 = torch.cholesky_inverse(Lc)
+    W64 = r_eff * torch.cholesky_solve(C64, Lc)
+    Lp = (L + 3) // 4 * 4
+    GC = torch.zeros(Q, Q + Lp, device=dev, dtype=torch.float32)
+    GC[:, :Q] = G64.float()
+    GC[:, Q:Q + L] = C64.float()
+    fac = ops.factor(GC, Q + Lp, Q, vs, True)
+    sc = fac.scal.cpu().numpy()
+    logdet = 2.0 * torch.log(torch.diagonal(Lc)).sum().item()
+    cond = float(torch.linalg.cond(B64))
+    print(f"[qspace Q={Q} L={L} r={r_eff:.1f} cond(B)={cond:.1e}] logdet err {abs(sc[S_LOGDETB] - logdet) / abs(logdet):.2e} "
+          f"trBinv err {abs(sc[S_TRBINV] - Binv64.trace().item()) / Binv64.trace().item():.2e} "
+          f"Binv err {rel_err(fac.Binv.cpu(), Binv64.cpu()):.2e}")
+    assert abs(sc[S_LOGDETB] - logdet) < 1e-6 * abs(logdet)
+    assert abs(sc[S_TRBINV] - Binv64.trace().item()) < 1e-4 * Binv64.trace().item()
+    assert rel_err(fac.Binv.cpu(), Binv64.cpu()) < 1e-4
+    W, _ = ops.solve_w(fac, GC[:, Q:], Q + Lp, Lp, L, n)
+    print(f"   W err {rel_err(W[:, :L].cpu(), W64.cpu()):.2e}")
+    assert rel_err(W[:, :L].cpu(), W64.cpu()) < 1e-4
