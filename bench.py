@@ -76,7 +76,7 @@ def cpu_reference_timing(cfg, budget_s: float = 20.0, rows: int | None = None):
         tc, _ = run(r_cal)
         per_row = max(tc - tb, 1e-6) / max(r_cal - min(256, N), 1)
         rows = int(max(1024, min(N, (budget_s - min(tb, budget_s * 0.5)) / per_row)))
-        rows = min(rows, 262144, N)
+        rows = min(rows, 131072, N)   # bounds host memory: the reference keeps ~6 N x Q fp32 matrices alive
     ts, _ = run(rows)
     a = max(ts - tb, 1e-9) / max(rows - min(256, N), 1)
     full = a * N + tb

@@ -1,36 +1,50 @@
-// Pass 1, pass 2 and Vb on the 5th-generation tensor cores as 3xTF32 (hi.hi + hi.lo + lo.hi), on CTA PAIRS.
+// Pass 1, pass 2, Vb and the Q-space block GEMMs on the 5th-generation tensor cores as 3xTF32
+// (hi.hi + hi.lo + lo.hi), on CTA PAIRS, with the M operand in TENSOR MEMORY.
 //
 // Every GEMM tile is 256 x 256 and belongs to a cluster of two CTAs (tcgen05 cta_group::2): each CTA stages ITS 128
-// rows of the M operand and ITS 128 columns of the N operand, the leader CTA issues M = 256, N = 256, K = 8 MMAs that
-// read both CTAs' shared memory, and each CTA's TMEM receives its 128 accumulator rows.  Per MMA a CTA's shared
-// memory serves 4 KB (A) + 4 KB (its half of B) instead of the 4 + 8 KB of a 1-CTA 128 x 256 MMA, and per k-row the
-// TMA / converter traffic drops by a third -- the 1-CTA version of this kernel was shared-memory-bandwidth bound
-// (MMA operand reads 96 B/clk + converter 64 B/clk + TMA 32 B/clk against 128 B/clk per SM; measured 69 % of the
-// tensor pipe); the pair version needs 64 + 43 + 21 B/clk.
+// rows of the M operand (A) and ITS 128 columns of the N operand (B); the leader CTA issues M = 256, K = 8 MMAs whose
+// A operand is read from both CTAs' TMEM and whose B operand is read from both CTAs' shared memory; each CTA's TMEM
+// receives its 128 accumulator rows.
 //
 //   pass 1:  D = sum_k A[k, m]^T B[k, n]   A = V[:, 256 tm ..], B = V[:, 256 tn ..] or X[:, 256 j ..]
-//            both operands row-major with the contraction over ROWS = MN-major UMMA operands; for tf32 the only
-//            MN-major layout is SWIZZLE_128B_BASE32B (atom = 32 floats x 4 k-rows, 32-byte chunks XORed with
+//            both operands are row-major with the contraction over ROWS.  B is an MN-major UMMA operand; for tf32
+//            the only MN-major layout is SWIZZLE_128B_BASE32B (atom = 32 floats x 4 k-rows, 32-byte chunks XORed with
 //            row % 4), which is what a TMA box {32 floats, BK rows} with SWIZZLE_128B_ATOM_32B writes:
 //            LBO = BK * 128 B between 32-float column groups, SBO = 512 B between 4-row k-groups, 1 KB per K = 8.
+//            A lands in shared memory the same way and is TRANSPOSED into TMEM by the converter warps (thread m reads
+//            column m of the tile: conflict-free, one 128-byte row per warp and k).
 //   rows  :  D = sum_k [A1 | A2][row, k] B[k, col]   (pass 2: A1 = V, B = W; Vb: A1 = V, A2 = Xb, B = [rL Binv; -W^T])
-//            A is K-major: TMA box {16 floats, 128 rows} with SWIZZLE_64B, SBO = 512 B, +32 B per K = 8 step.
+//            A lands K-major: TMA box {16 floats, 128 rows} with SWIZZLE_64B; thread m reads its row (4 x 128 bit).
+//
+// Why A lives in TMEM.  With both operands in shared memory a 16-row stage costs, per CTA, 48 KB of MMA operand
+// reads + 32 KB of converter traffic + 16 KB of TMA writes = 848 shared-memory wavefronts against 768 tensor-pipe
+// cycles: the kernel was shared-memory-bandwidth bound (measured: 1114 cycles per stage, tensor pipe 70 % active).
+// A from TMEM removes its 24 KB of operand reads and the 8 KB lo-plane store: 512 wavefronts per stage.
 //
 // Numerics (measured on B200, experiments/tc/exp1_gram.cu): kind::tf32 TRUNCATES fp32 operands and the TMEM
 // accumulator is rounded toward zero after every MMA.  Hence
-//   * the raw fp32 tile is the hi operand as it stands (the hardware truncation is the split); the converter warps
-//     only write lo = rn_tf32(a - trunc_tf32(a));
-//   * accumulation in TMEM is limited to WINDOWS of kWin stages; inside a window the small cross terms (hi.lo, lo.hi)
-//     of ALL its stages are issued first, while the accumulator is still tiny (their truncation error is negligible
-//     there), and the hi.hi terms last, so only 2 kWin truncations per window happen at full magnitude;
-//   * windows ping-pong between two TMEM buffers and are summed in fp32 registers (round-to-nearest) by the drain warps.
+//   * the raw fp32 value is the hi operand as it stands (the hardware truncation is the split); the converter warps
+//     only add lo = rn_tf32(a - trunc_tf32(a));
+//   * accumulation in TMEM is limited to WINDOWS of 4 stages (64 k-rows); inside a window the MMAs go out in groups
+//     of 2 stages, cross terms (hi.lo, lo.hi) first, hi.hi last, so the small terms are added while the accumulator
+//     is small; finished windows are added in fp32 registers (round-to-nearest) by the drain warps.
+//
+// TMEM map (512 columns): [0, 256) ONE accumulator tile, used as two independent 128-column halves whose windows are
+// staggered by half a window: while the drain warps empty one half the tensor pipe works on the other, which gives
+// the overlap of a double-buffered accumulator in half the columns (N = 128 MMAs cost nothing extra once A comes from
+// TMEM: B is not re-read).  [256, 512) ring of 8 A slots: 16 columns hi + 16 columns lo per 16-row stage.
 //
 // Warp roles per CTA (512 threads, setmaxnreg re-balanced): warp 0 TMA producer (own halves), warp 1 MMA issuer
-// (leader CTA only) + TMEM owner, warps 4-7 converters, warps 8-15 drain / epilogue of the CTA's own 128 rows.
-// Barriers: full[s] (local TMA -> local converters), conv[s] (converters of BOTH CTAs -> leader), empty[s], lo_empty[s]
-// and tfull[b] (MMA commit, multicast to both CTAs), tempty[b] (drain warps of both CTAs -> leader).
+// (leader CTA only) + TMEM owner, warps 4-7 converters (thread = A row = TMEM lane), warps 8-15 drain / epilogue.
+// Rings: raw tiles (TMA -> converter -> MMA, 16 KB: A raw + B raw = B hi) and lo slots (B lo plane in shared memory +
+// the A slot in TMEM; converter -> MMA).  Barriers: full[s] (local TMA -> local converters), conv[s] (converters of
+// BOTH CTAs -> leader), empty[s], lo_empty[s] and tfull[h] (MMA commit, multicast to both CTAs), tempty[h] (drain
+// warps of both CTAs -> leader).  Remote arrives use the default .release.cta semantics on purpose (.release.cluster
+// compiles to MEMBAR.ALL.GPU per arrive).
 // Pass 1 is persistent over (tile, k-split) units with a deterministic split-K: every unit writes its own partial
 // tile, tc_reduce_kernel sums them in a fixed order (fp64) and tc_mirror_kernel fills the upper triangle of G.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -41,28 +55,28 @@ using namespace tc;
 
 namespace {
 
-#ifndef GPP_TC_WIN
-#define GPP_TC_WIN 4
-#endif
 #ifndef GPP_TC_RAW
-#define GPP_TC_RAW 9     // raw (fp32 = hi) tiles in flight: TMA -> converter -> MMA
+#define GPP_TC_RAW 10    // raw tiles in flight: TMA -> converter -> MMA (B hi is read from them)
 #endif
 #ifndef GPP_TC_LO
-#define GPP_TC_LO 4      // lo planes in flight: converter -> MMA
+#define GPP_TC_LO 8      // lo slots in flight (B lo in shared memory + A hi/lo in TMEM): converter -> MMA
 #endif
 constexpr int TM = 256, TN = 256;   // tile of a CTA pair
 constexpr int HM = 128, HN = 128;   // what one CTA stages of it
+constexpr int TBK = 16, kRaw = GPP_TC_RAW, kLo = GPP_TC_LO;
 #ifndef GPP_TC_GROUP
-#define GPP_TC_GROUP 2
+#define GPP_TC_GROUP 4
 #endif
-constexpr int TBK = 16, kRaw = GPP_TC_RAW, kLo = GPP_TC_LO, kWin = GPP_TC_WIN, kGroup = GPP_TC_GROUP;
+#ifndef GPP_TC_WINGROUPS
+#define GPP_TC_WINGROUPS 1
+#endif
+constexpr int kGroup = GPP_TC_GROUP;           // stages per issue group (cross terms of the group first, then hi.hi)
+constexpr int kWinGroups = GPP_TC_WINGROUPS;   // groups per accumulation window (window = 4 stages = 64 k-rows)
 constexpr int kABytes = HM * TBK * 4, kBBytes = HN * TBK * 4, kRawBytes = kABytes + kBBytes;   // 8 K + 8 K
-// Two rings: a raw tile is occupied from the TMA issue until its last MMA (TMA latency + conversion + MMA), its lo
-// plane only from the conversion on, so the lo ring can be much shorter than the raw ring and the shared memory
-// goes into TMA prefetch depth instead.
 constexpr int kTcThreads = 512;
-constexpr int kSmemBytes = (kRaw + kLo) * kRawBytes + 1024 /*align*/ + 512 /*barriers*/;
-static_assert(kGroup >= 1 && kGroup <= kWin && kGroup < kLo && kLo <= kRaw, "a group must fit in the lo ring with room to convert ahead");
+constexpr int kSmemBytes = kRaw * kRawBytes + kLo * kBBytes + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int kAccCols = 256, kASlotCols = 32;   // TMEM: accumulator tile, then kLo A slots (16 hi + 16 lo columns)
+static_assert(kGroup < kLo && kLo <= kRaw && kAccCols + kLo * kASlotCols <= 512, "ring sizes");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // Optional role profiling (-DGPP_TC_PROF): cycles each role spends waiting on its barriers, per CTA.
@@ -120,7 +134,7 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 
 // ---- pieces shared by the two kernels ----------------------------------------------------------------------
 __device__ __forceinline__ TcShared* tc_prologue(uint8_t* base, uint32_t& tmem) {
-  TcShared* sm = reinterpret_cast<TcShared*>(base + (kRaw + kLo) * kRawBytes);
+  TcShared* sm = reinterpret_cast<TcShared*>(base + kRaw * kRawBytes + kLo * kBBytes);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRaw; ++s) {
       mbar_init(&sm->full[s], 1);
@@ -130,9 +144,9 @@ __device__ __forceinline__ TcShared* tc_prologue(uint8_t* base, uint32_t& tmem) 
       mbar_init(&sm->conv[s], 8);     // 4 converter warps x 2 CTAs (used in the leader)
       mbar_init(&sm->lo_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&sm->tfull[b], 1);
-      mbar_init(&sm->tempty[b], 16);  // 8 drain warps x 2 CTAs (used in the leader)
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&sm->tfull[h], 1);
+      mbar_init(&sm->tempty[h], 16);  // 8 drain warps x 2 CTAs (used in the leader)
     }
     fence_mbar_init();
   }
@@ -150,100 +164,143 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem) {
   if ((threadIdx.x >> 5) == 1) tmem_dealloc_pair(tmem, 512);
 }
 
-// converter warps: wait for the raw tile of stage s, write the lo plane, tell the leader
-__device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint32_t conv0_leader, uint32_t it,
-                                              unsigned long long& pw0, unsigned long long& pw1) {
-  const int t = threadIdx.x - 128, lane = threadIdx.x & 31;
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// Converter warps (threads 128..255; thread t = A row t of this CTA = TMEM lane t): wait for the raw tile of ring
+// position `it`, move A (hi = raw, lo) into the TMEM slot, write the lo plane of B next to nothing else in shared
+// memory, tell the leader.  Explicit shared-space accesses, all loads before the first store (through generic
+// pointers the compiler kept every load behind the previous store).
+// A_MN: the raw A tile is MN-major (pass 1: [k-row][32-float group], SWIZZLE_128B_BASE32B) or K-major (row GEMM:
+// [row][16 floats], SWIZZLE_64B).
+template <bool A_MN>
+__device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint32_t tmem, uint32_t conv0_leader,
+                                              uint32_t it, unsigned long long& pw0, unsigned long long& pw1) {
+  const int t = threadIdx.x - 128, lane = threadIdx.x & 31, wq = t >> 5;
   const int s = it % kRaw, sl = it % kLo;
   PROF_WAIT(pw0, mbar_wait(&sm->full[s], (it / kRaw) & 1));
+  const uint32_t raw = smem_u32(base + s * kRawBytes);
+  uint32_t ahi[TBK], alo[TBK];
+  if (A_MN) {
+    // element (k, m = t): group wq, k-row k, 32-byte chunk ((lane / 8) ^ (k % 4)), word lane % 8
+    const uint32_t a0 = raw + wq * (TBK * 128) + (lane & 7) * 4;
+#pragma unroll
+    for (int k = 0; k < TBK; ++k)
+      ahi[k] = __float_as_uint(lds_f32(a0 + k * 128 + (((lane >> 3) ^ (k & 3)) << 5)));
+  } else {
+    // row t: 64 bytes, 16-byte chunk c stored at c ^ ((t / 2) % 4)
+    const uint32_t a0 = raw + t * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 v = lds_f32x4(a0 + ((c ^ ((t >> 1) & 3)) << 4));
+      ahi[4 * c + 0] = __float_as_uint(v.x); ahi[4 * c + 1] = __float_as_uint(v.y);
+      ahi[4 * c + 2] = __float_as_uint(v.z); ahi[4 * c + 3] = __float_as_uint(v.w);
+    }
+  }
+  float4 bv[kBBytes / 16 / 128];
+#pragma unroll
+  for (int i = 0; i < kBBytes / 16 / 128; ++i) bv[i] = lds_f32x4(raw + kABytes + t * 16 + i * 2048);
+#pragma unroll
+  for (int k = 0; k < TBK; ++k) alo[k] = __float_as_uint(tf32_lo(__uint_as_float(ahi[k])));
   PROF_WAIT(pw1, mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1));
-  // explicit shared-space accesses, all loads before the first store: through generic pointers the compiler emitted
-  // LD.E / ST.E and kept every load behind the previous store (possible aliasing), i.e. eight exposed shared-memory
-  // latencies per stage, which made these warps the bottleneck of the whole pipeline
-  const uint32_t raw = smem_u32(base + s * kRawBytes) + t * 16, lo = smem_u32(base + (kRaw + sl) * kRawBytes) + t * 16;
-  constexpr int kIters = kRawBytes / 16 / 128;
-  float4 v[kIters];
+  tcgen05_fence_after();
+  const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + kAccCols + sl * kASlotCols;
+  tmem_st_32x16(ta, ahi);
+  tmem_st_32x16(ta + TBK, alo);
+  const uint32_t blo = smem_u32(base + kRaw * kRawBytes + sl * kBBytes) + t * 16;
 #pragma unroll
-  for (int i = 0; i < kIters; ++i)
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
-                 : "r"(raw + i * 2048));
-#pragma unroll
-  for (int i = 0; i < kIters; ++i) {
-    const float4 l = make_float4(tf32_lo(v[i].x), tf32_lo(v[i].y), tf32_lo(v[i].z), tf32_lo(v[i].w));
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + i * 2048), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
+  for (int i = 0; i < kBBytes / 16 / 128; ++i) {
+    const float4 l = make_float4(tf32_lo(bv[i].x), tf32_lo(bv[i].y), tf32_lo(bv[i].z), tf32_lo(bv[i].w));
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blo + i * 2048), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
                  : "memory");
   }
+  tmem_wait_st();
+  tcgen05_fence_before();
   fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(conv0_leader + 8u * sl);
 }
 
-// MMA issuer (one thread of the leader): one window of `wst` stages starting at ring position `it` into TMEM buffer d.
-// The window is issued in GROUPS of kGroup stages: wait for the group's stages, issue the cross terms (hi.lo, lo.hi)
-// of the whole group, then its hi.hi terms, releasing each stage's slot right after its hi.hi MMAs.
-// A_MN: A operand MN-major (pass 1) or K-major (rows kernel).
-template <bool A_MN>
-__device__ __forceinline__ void issue_window(uint8_t* base, TcShared* sm, uint32_t d, uint32_t it, int wst,
-                                             unsigned long long& pw1) {
-  constexpr uint32_t idesc = umma_idesc_tf32(TM, TN, A_MN, true);
-  uint32_t acc = 0;
-  for (int g0 = 0; g0 < wst; g0 += kGroup) {
-    const int g1 = min(wst, g0 + kGroup);
-    for (int j = g0; j < g1; ++j) {
-      // each stage's cross terms go out as soon as that stage is converted (the pipe has work while the next converts)
-      PROF_WAIT(pw1, mbar_wait_cluster(&sm->conv[(it + j) % kLo], ((it + j) / kLo) & 1));
-      tcgen05_fence_after();
-      const uint32_t a_hi = smem_u32(base + ((it + j) % kRaw) * kRawBytes), b_hi = a_hi + kABytes;
-      const uint32_t a_lo = smem_u32(base + (kRaw + (it + j) % kLo) * kRawBytes), b_lo = a_lo + kABytes;
+// ---- window schedule ------------------------------------------------------------------------------------------
+// A unit of `nst` stages is issued in groups of kGroup stages; the accumulator collects windows of kWinGroups groups.
+// Both the issuer and the drain warps walk this schedule.
+__device__ __forceinline__ bool win_begins(int g) { return (g % kWinGroups) == 0; }
+__device__ __forceinline__ bool win_ends(int g, int ngroups) { return g == ngroups - 1 || (g % kWinGroups) == kWinGroups - 1; }
+
+// MMA issuer (one thread of the leader): group g of a unit (stages [it, it + gst)).
+// wc: windows issued so far (barrier phase).
+__device__ __forceinline__ void issue_group(uint8_t* base, TcShared* sm, uint32_t tmem, uint32_t it, int gst, int g,
+                                            int ngroups, uint32_t& wc, unsigned long long& pw0,
+                                            unsigned long long& pw1) {
+  constexpr uint32_t idesc = umma_idesc_tf32(TM, TN, false, true);
+  const uint32_t d = tmem;
+  uint32_t acc = 1;
+  if (win_begins(g)) {
+    PROF_WAIT(pw0, mbar_wait_cluster(&sm->tempty[0], (wc & 1) ^ 1));
+    tcgen05_fence_after();
+    acc = 0;
+  }
+  for (int j = 0; j < gst; ++j) {   // cross terms of the group first: they land in a still-small accumulator
+    const int sl = (it + j) % kLo;
+    PROF_WAIT(pw1, mbar_wait_cluster(&sm->conv[sl], ((it + j) / kLo) & 1));
+    tcgen05_fence_after();
+    const uint32_t b_hi = smem_u32(base + ((it + j) % kRaw) * kRawBytes) + kABytes;
+    const uint32_t b_lo = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
+    const uint32_t a_hi = tmem + kAccCols + sl * kASlotCols, a_lo = a_hi + TBK;
 #pragma unroll
-      for (int kk = 0; kk < TBK / 8; ++kk) {
-        const uint64_t dah = A_MN ? umma_desc(a_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32)
-                                  : umma_desc(a_hi + kk * 32, 16, 512, kLayoutSw64);
-        const uint64_t dal = A_MN ? umma_desc(a_lo + kk * 1024, TBK * 128, 512, kLayoutSw128Base32)
-                                  : umma_desc(a_lo + kk * 32, 16, 512, kLayoutSw64);
-        const uint64_t dbh = umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
-        const uint64_t dbl = umma_desc(b_lo + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
-        umma_tf32_pair(d, dah, dbl, idesc, acc);
-        umma_tf32_pair(d, dal, dbh, idesc, 1);
-        acc = 1;
-      }
+    for (int kk = 0; kk < TBK / 8; ++kk) {
+      const uint64_t dbh = umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
+      const uint64_t dbl = umma_desc(b_lo + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
+      umma_tf32_pair_ts(d, a_hi + kk * 8, dbl, idesc, acc);
+      umma_tf32_pair_ts(d, a_lo + kk * 8, dbh, idesc, 1);
+      acc = 1;
     }
-    for (int j = g0; j < g1; ++j) {
-      const int s = (it + j) % kRaw;
-      const uint32_t a_hi = smem_u32(base + s * kRawBytes), b_hi = a_hi + kABytes;
+  }
+  for (int j = 0; j < gst; ++j) {   // then the hi.hi terms
+    const int s = (it + j) % kRaw, sl = (it + j) % kLo;
+    const uint32_t b_hi = smem_u32(base + s * kRawBytes) + kABytes;
+    const uint32_t a_hi = tmem + kAccCols + sl * kASlotCols;
 #pragma unroll
-      for (int kk = 0; kk < TBK / 8; ++kk) {
-        const uint64_t dah = A_MN ? umma_desc(a_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32)
-                                  : umma_desc(a_hi + kk * 32, 16, 512, kLayoutSw64);
-        const uint64_t dbh = umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
-        umma_tf32_pair(d, dah, dbh, idesc, 1);
-      }
-      umma_commit_pair(&sm->empty[s], 3);                      // raw tile and lo plane free in both CTAs
-      umma_commit_pair(&sm->lo_empty[(it + j) % kLo], 3);
-    }
+    for (int kk = 0; kk < TBK / 8; ++kk)
+      umma_tf32_pair_ts(d, a_hi + kk * 8, umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32), idesc, 1);
+    umma_commit_pair(&sm->empty[s], 3);       // raw tile, B lo plane and A slot are free in both CTAs
+    umma_commit_pair(&sm->lo_empty[sl], 3);
+  }
+  if (win_ends(g, ngroups)) {
+    umma_commit_pair(&sm->tfull[0], 3);
+    ++wc;
   }
 }
 
-// drain warps: add one finished window (this CTA's 128 rows x this warp's 128 columns) into registers
-__device__ __forceinline__ void drain_window(TcShared* sm, uint32_t tmem, uint32_t tempty0_leader, uint32_t wc,
-                                             float (&acc)[128], unsigned long long& pw0) {
+// Drain warps: after a group that ends a window, add the window (this CTA's 128 rows x this warp's 128 columns) into
+// registers.
+__device__ __forceinline__ void drain_group(TcShared* sm, uint32_t tmem, uint32_t tempty0_leader, int g, int ngroups,
+                                            uint32_t& wc, float (&acc)[128], unsigned long long& pw0) {
+  if (!win_ends(g, ngroups)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-  const int half = (warp - 8) >> 2;
-  const uint32_t buf = wc & 1;
-  PROF_WAIT(pw0, mbar_wait(&sm->tfull[buf], (wc >> 1) & 1));
+  const int cb = (warp - 8) >> 2;
+  PROF_WAIT(pw0, mbar_wait(&sm->tfull[0], wc & 1));
+  ++wc;
   tcgen05_fence_after();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float v[32];
-    tmem_ld_32x32(tmem + lane_addr + buf * TN + half * 128 + c * 32, v);
+    tmem_ld_32x32(tmem + lane_addr + cb * 128 + c * 32, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
   }
   tcgen05_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive_cluster(tempty0_leader + 8u * buf);
+  if (lane == 0) mbar_arrive_cluster(tempty0_leader);
 }
 
 // =====================================================================================================
@@ -299,13 +356,11 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
         const int64_t r0 = (int64_t)split * p.rows_per_split;
         const int64_t r1 = min(p.n, r0 + p.rows_per_split);
         const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
-        for (int st0 = 0; st0 < nst; st0 += kWin, ++wc) {
-          const uint32_t buf = wc & 1;
-          PROF_WAIT(pw0, mbar_wait_cluster(&sm->tempty[buf], ((wc >> 1) & 1) ^ 1));
-          const int wst = min(kWin, nst - st0);
-          issue_window<true>(base, sm, tmem + buf * TN, it, wst, pw1);
-          umma_commit_pair(&sm->tfull[buf], 3);   // window complete in both CTAs' TMEM
-          it += wst;
+        const int ngroups = (nst + kGroup - 1) / kGroup;
+        for (int g = 0; g < ngroups; ++g) {
+          const int gst = min(kGroup, nst - g * kGroup);
+          issue_group(base, sm, tmem, it, gst, g, ngroups, wc, pw0, pw1);
+          it += gst;
         }
       }
       PROF_STORE(1);
@@ -321,7 +376,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       const int64_t r0 = (int64_t)split * p.rows_per_split;
       const int64_t r1 = min(p.n, r0 + p.rows_per_split);
       const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
-      for (int st = 0; st < nst; ++st, ++it) convert_stage(base, sm, conv0, it, pw0, pw1);
+      for (int st = 0; st < nst; ++st, ++it) convert_stage<true>(base, sm, tmem, conv0, it, pw0, pw1);
     }
     if (threadIdx.x == 128) PROF_STORE(2);
   } else {
@@ -329,19 +384,20 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
     setmaxnreg_inc<184>();
     PROF_DECL;
     const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
-    const int q = warp & 3, half = (warp - 8) >> 2;
+    const int q = warp & 3, cb = (warp - 8) >> 2;
     uint32_t wc = 0;
     for (int u = pair; u < nunits; u += npairs) {
       const int split = u / p.tiles, tile = u - split * p.tiles;
       const int64_t r0 = (int64_t)split * p.rows_per_split;
       const int64_t r1 = min(p.n, r0 + p.rows_per_split);
       const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
+      const int ngroups = (nst + kGroup - 1) / kGroup;
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-      for (int st0 = 0; st0 < nst; st0 += kWin, ++wc) drain_window(sm, tmem, tempty0, wc, acc, pw0);
+      for (int g = 0; g < ngroups; ++g) drain_group(sm, tmem, tempty0, g, ngroups, wc, acc, pw0);
       float* out = p.partial + ((size_t)tile * p.splits + split) * (size_t)(TM * TN) +
-                   (size_t)(rank * HM + q * 32 + lane) * TN + half * 128;
+                   (size_t)(rank * HM + q * 32 + lane) * TN + cb * 128;
 #pragma unroll
       for (int i = 0; i < 128; i += 4)
         *reinterpret_cast<float4*>(out + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
@@ -482,20 +538,21 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             tma_load_2d(dst + kABytes + g * (TBK * 128), &tmB, bcol + g * 32, kb, &sm->full[s]);
         }
       }
+      PROF_STORE(0);
     } else if (warp == 1 && lane == 0 && rank == 0) {
       PROF_DECL;
       uint32_t it = 0, wc = 0;
       for (int64_t u = pair; u < nunits; u += npairs) {
         const RowsUnit un = rows_unit(p, u, nst);
-        for (int st0 = un.k_begin; st0 < un.k_end; st0 += kWin, ++wc) {
-          const uint32_t buf = wc & 1;
-          PROF_WAIT(pw0, mbar_wait_cluster(&sm->tempty[buf], ((wc >> 1) & 1) ^ 1));
-          const int wst = min(kWin, un.k_end - st0);
-          issue_window<false>(base, sm, tmem + buf * TN, it, wst, pw1);
-          umma_commit_pair(&sm->tfull[buf], 3);
-          it += wst;
+        const int ust = un.k_end - un.k_begin;
+        const int ngroups = (ust + kGroup - 1) / kGroup;
+        for (int g = 0; g < ngroups; ++g) {
+          const int gst = min(kGroup, ust - g * kGroup);
+          issue_group(base, sm, tmem, it, gst, g, ngroups, wc, pw0, pw1);
+          it += gst;
         }
       }
+      PROF_STORE(1);
     }
   } else if (warp < 8) {
     setmaxnreg_dec<96>();
@@ -504,13 +561,14 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     uint32_t it = 0;
     for (int64_t u = pair; u < nunits; u += npairs) {
       const RowsUnit un = rows_unit(p, u, nst);
-      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_stage(base, sm, conv0, it, pw0, pw1);
+      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_stage<false>(base, sm, tmem, conv0, it, pw0, pw1);
     }
+    if (threadIdx.x == 128) PROF_STORE(2);
   } else {
     setmaxnreg_inc<184>();
     PROF_DECL;
     const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
-    const int q = warp & 3, half = (warp - 8) >> 2;
+    const int q = warp & 3, cb = (warp - 8) >> 2;
     uint32_t wc = 0;
     float alpha = p.alpha_host;
     if (p.mode == 0 && p.scal) alpha = (float)(1.0 / p.scal[GPP_S_VN]);
@@ -518,13 +576,15 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const RowsUnit un = rows_unit(p, u, nst);
       const int64_t rt = un.rt;
       const int ct = un.ct;
+      const int ust = un.k_end - un.k_begin;
+      const int ngroups = (ust + kGroup - 1) / kGroup;
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-      for (int st0 = un.k_begin; st0 < un.k_end; st0 += kWin, ++wc) drain_window(sm, tmem, tempty0, wc, acc, pw0);
-      // ---- epilogue for this unit: this CTA's 128 rows
+      for (int g = 0; g < ngroups; ++g) drain_group(sm, tmem, tempty0, g, ngroups, wc, acc, pw0);
+      // ---- epilogue for this unit: this CTA's 128 rows, this warp's 128 columns
       const int64_t row = rt * TM + rank * HM + q * 32 + lane;
-      const int col0 = ct * TN + half * 128;
+      const int col0 = ct * TN + cb * 128;
       float xb2 = 0.f;
       if (row < (un.batch == p.batches - 1 ? p.n_last : p.n)) {
         if (p.mode == 0) {
@@ -547,7 +607,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               xb2 = fmaf(o.z, o.z, xb2); xb2 = fmaf(o.w, o.w, xb2);
             }
           }
-          if (p.quad_part) p.quad_part[(int64_t)(ct * 2 + half) * p.n + row] = quad;
+          if (p.quad_part) p.quad_part[(int64_t)(ct * 2 + cb) * p.n + row] = quad;
         } else {
           float* orow = p.out + un.batch * p.out_step + row * p.ldo + col0;
 #pragma unroll
@@ -562,6 +622,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         if (lane == 0) p.xb2_part[u * 16 + rank * 8 + (warp - 8)] = (double)s;
       }
     }
+    if (threadIdx.x == 256) PROF_STORE(3);
   }
   tc_epilogue(tmem);
 }
@@ -678,6 +739,10 @@ void pass1_geometry(int64_t n, int Q, int L, bool skip_g, Pass1Params& p) {
       best_eff = eff;
       best = s;
     }
+  }
+  if (const char* e = getenv("GPP_TC_SPLIT_ROWS")) {   // experiment knob: target rows per split
+    const long long r = atoll(e);
+    if (r >= 512) best = (int)ceil_div(n > 0 ? n : 1, r);
   }
   p.rows_per_split = ceil_div(ceil_div(n > 0 ? n : 1, best), TBK) * TBK;
   p.splits = (int)ceil_div(n > 0 ? n : 1, p.rows_per_split);

@@ -202,6 +202,29 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
+// ------------------------------------------------------------------ A operand in tensor memory
+// 32 lanes x 16 consecutive 32-bit columns <- 16 registers per thread (thread t of the warp = lane base + t).
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem] on a CTA pair: A (M = 256, K = 8, one 32-bit column per k) is read from the SAME
+// TMEM columns of both CTAs (each holds its 128 rows), B from both CTAs' shared memory.
+__device__ __forceinline__ void umma_tf32_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ 3xTF32 operand split
 // hi = fp32 rounded to tf32 (nearest), lo = tf32(a - hi): a.b ~= hi.hi + hi.lo + lo.hi with ~2^-21 relative error.
 __device__ __forceinline__ float tf32_rn(float a) {
