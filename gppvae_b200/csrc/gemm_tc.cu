@@ -75,6 +75,19 @@ constexpr int kWinGroups = GPP_TC_WINGROUPS;   // groups per accumulation window
 constexpr int kABytes = HM * TBK * 4, kBBytes = HN * TBK * 4, kRawBytes = kABytes + kBBytes;   // 8 K + 8 K
 constexpr int kTcThreads = 512;
 constexpr int kSmemBytes = kRaw * kRawBytes + kLo * kBBytes + 1024 /*align*/ + 512 /*barriers*/;
+#ifndef GPP_TC_F16X
+#define GPP_TC_F16X 1    // 1: correction terms (hi.lo, lo.hi) as ONE K = 16 fp16 MMA each; 0: as two K = 8 tf32 MMAs each
+#endif
+#ifndef GPP_TC_F16_PACK
+#define GPP_TC_F16_PACK 0   // which half of a TMEM column holds the even k of an fp16 A pair (bring-up knob)
+#endif
+#ifndef GPP_TC_F16_LBO
+#define GPP_TC_F16_LBO 2048
+#endif
+#ifndef GPP_TC_F16_SBO
+#define GPP_TC_F16_SBO 1024
+#endif
+constexpr float kHiScale = 0.015625f, kLoScale = 64.f;   // fp16 hi factor a 2^-6, fp16 lo factor lo 2^6: product unscaled
 constexpr int kAccCols = 256, kASlotCols = 32;   // TMEM: accumulator tile, then kLo A slots (16 hi + 16 lo columns)
 static_assert(kGroup < kLo && kLo <= kRaw && kAccCols + kLo * kASlotCols <= 512, "ring sizes");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -188,7 +201,10 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint3
   const int s = it % kRaw, sl = it % kLo;
   PROF_WAIT(pw0, mbar_wait(&sm->full[s], (it / kRaw) & 1));
   const uint32_t raw = smem_u32(base + s * kRawBytes);
-  uint32_t ahi[TBK], alo[TBK];
+  uint32_t ahi[TBK];
+#if !GPP_TC_F16X
+  uint32_t alo[TBK];
+#endif
   if (A_MN) {
     // element (k, m = t): group wq, k-row k, 32-byte chunk ((lane / 8) ^ (k % 4)), word lane % 8
     const uint32_t a0 = raw + wq * (TBK * 128) + (lane & 7) * 4;
@@ -205,6 +221,54 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint3
       ahi[4 * c + 2] = __float_as_uint(v.z); ahi[4 * c + 3] = __float_as_uint(v.w);
     }
   }
+#if GPP_TC_F16X
+  // B: float4 (k-row kb, 32-float group g32, 16-byte position qb) chosen so that 16 lanes cover the 64 columns of one
+  // fp16 row: conflict-free 128-bit loads here and conflict-free 64-bit stores into the fp16 planes below
+  float4 bv[4];
+  const int qb = lane & 7, bb = (lane >> 3) & 1, kpar = lane >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = wq * 4 + i, jj = m & 1, kb = 2 * (m >> 1) + kpar;
+    bv[i] = lds_f32x4(raw + kABytes + (2 * jj + bb) * (TBK * 128) + kb * 128 + qb * 16);
+  }
+  // A: hi32 = raw (tf32 hh term); fp16 pairs of a 2^-6 and of (a - trunc_tf32(a)) 2^6 for the correction terms
+  uint32_t a16[TBK];
+#pragma unroll
+  for (int c = 0; c < TBK / 2; ++c) {
+    const float x0 = __uint_as_float(ahi[2 * c]), x1 = __uint_as_float(ahi[2 * c + 1]);
+    const float l0 = x0 - __uint_as_float(ahi[2 * c] & 0xFFFFE000u), l1 = x1 - __uint_as_float(ahi[2 * c + 1] & 0xFFFFE000u);
+#if GPP_TC_F16_PACK == 0
+    a16[c] = pack_f16x2(x0 * kHiScale, x1 * kHiScale);
+    a16[TBK / 2 + c] = pack_f16x2(l0 * kLoScale, l1 * kLoScale);
+#else
+    a16[c] = pack_f16x2(x1 * kHiScale, x0 * kHiScale);
+    a16[TBK / 2 + c] = pack_f16x2(l1 * kLoScale, l0 * kLoScale);
+#endif
+  }
+  PROF_WAIT(pw1, mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1));
+  tcgen05_fence_after();
+  const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + kAccCols + sl * kASlotCols;
+  tmem_st_32x16(ta, ahi);
+  tmem_st_32x16(ta + TBK, a16);
+  // B fp16 planes (hi plane at +0, lo plane at +4 KB), each MN-major SWIZZLE_128B: 64-column group g at g * 2 KB,
+  // k-row k at (k / 8) * 1 KB + (k % 8) * 128 B, 16-byte chunk ((c % 64) / 8) ^ (k % 8), element (c % 8) * 2 B
+  const uint32_t bplane = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = wq * 4 + i, jj = m & 1, kb = 2 * (m >> 1) + kpar;
+    const int chunk = 4 * bb + ((qb >> 1) ^ (kb & 3));          // logical 8-column chunk within the 64-column group
+    const uint32_t dst = bplane + jj * 2048 + (kb >> 3) * 1024 + (kb & 7) * 128 + ((chunk ^ (kb & 7)) << 4) + (qb & 1) * 8;
+    const float4 v = bv[i];
+    const uint32_t h0 = pack_f16x2(v.x * kHiScale, v.y * kHiScale), h1 = pack_f16x2(v.z * kHiScale, v.w * kHiScale);
+    const float lx = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    const float ly = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    const float lz = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    const float lw = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    const uint32_t l0 = pack_f16x2(lx * kLoScale, ly * kLoScale), l1 = pack_f16x2(lz * kLoScale, lw * kLoScale);
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kBBytes / 2), "r"(l0), "r"(l1) : "memory");
+  }
+#else
   float4 bv[kBBytes / 16 / 128];
 #pragma unroll
   for (int i = 0; i < kBBytes / 16 / 128; ++i) bv[i] = lds_f32x4(raw + kABytes + t * 16 + i * 2048);
@@ -222,6 +286,7 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint3
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blo + i * 2048), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
                  : "memory");
   }
+#endif
   tmem_wait_st();
   tcgen05_fence_before();
   fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -252,6 +317,15 @@ __device__ __forceinline__ void issue_group(uint8_t* base, TcShared* sm, uint32_
     const int sl = (it + j) % kLo;
     PROF_WAIT(pw1, mbar_wait_cluster(&sm->conv[sl], ((it + j) / kLo) & 1));
     tcgen05_fence_after();
+#if GPP_TC_F16X
+    // one K = 16 fp16 MMA per correction term: (a 2^-6) . (b_lo 2^6) and (a_lo 2^6) . (b 2^-6)
+    constexpr uint32_t idesc16 = umma_idesc_f16(TM, TN, false, true);
+    const uint32_t b16 = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
+    const uint32_t a16 = tmem + kAccCols + sl * kASlotCols + TBK;
+    umma_f16_pair_ts(d, a16, umma_desc(b16 + kBBytes / 2, GPP_TC_F16_LBO, GPP_TC_F16_SBO, kLayoutSw128), idesc16, acc);
+    umma_f16_pair_ts(d, a16 + TBK / 2, umma_desc(b16, GPP_TC_F16_LBO, GPP_TC_F16_SBO, kLayoutSw128), idesc16, 1);
+    acc = 1;
+#else
     const uint32_t b_hi = smem_u32(base + ((it + j) % kRaw) * kRawBytes) + kABytes;
     const uint32_t b_lo = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
     const uint32_t a_hi = tmem + kAccCols + sl * kASlotCols, a_lo = a_hi + TBK;
@@ -263,6 +337,7 @@ __device__ __forceinline__ void issue_group(uint8_t* base, TcShared* sm, uint32_
       umma_tf32_pair_ts(d, a_lo + kk * 8, dbh, idesc, 1);
       acc = 1;
     }
+#endif
   }
   for (int j = 0; j < gst; ++j) {   // then the hi.hi terms
     const int s = (it + j) % kRaw, sl = (it + j) % kLo;

@@ -225,6 +225,29 @@ __device__ __forceinline__ void umma_tf32_pair_ts(uint32_t tmem_d, uint32_t tmem
       : "memory");
 }
 
+// ------------------------------------------------------------------ fp16 correction terms
+// Instruction descriptor for kind::f16 with fp16 A and B, fp32 accumulate (same fields as the tf32 one, A/B format 0).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem, fp16 pairs, K = 16 in 8 columns] . B[smem, fp16] on a CTA pair.
+__device__ __forceinline__ void umma_f16_pair_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// {lo16 = fp16(a), hi16 = fp16(b)} (round to nearest)
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // ------------------------------------------------------------------ 3xTF32 operand split
 // hi = fp32 rounded to tf32 (nearest), lo = tf32(a - hi): a.b ~= hi.hi + hi.lo + lo.hi with ~2^-21 relative error.
 __device__ __forceinline__ float tf32_rn(float a) {
