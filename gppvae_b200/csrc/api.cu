@@ -45,7 +45,7 @@ using namespace gpp;
 
 extern "C" int gpp_version(void) { return 100; }
 extern "C" const char* gpp_last_error(void) { return g_last_error.c_str(); }
-extern "C" const char* gpp_gemm_engine(void) { return "tcgen05-3xtf32"; }
+extern "C" const char* gpp_gemm_engine(void) { return "tcgen05-tf32+2xf16"; }
 extern "C" uint64_t gpp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------ pass 1

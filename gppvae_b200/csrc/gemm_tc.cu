@@ -1,8 +1,8 @@
-// Pass 1, pass 2, Vb and the Q-space block GEMMs on the 5th-generation tensor cores as 3xTF32
-// (hi.hi + hi.lo + lo.hi), on CTA PAIRS, with the M operand in TENSOR MEMORY.
+// Pass 1, pass 2, Vb and the Q-space block GEMMs on the 5th-generation tensor cores, fp32-accurate through a 3-term
+// operand split  a.b ~= hi(a).hi(b) + a.lo(b) + lo(a).b,  on CTA PAIRS, with the M operand in TENSOR MEMORY.
 //
 // Every GEMM tile is 256 x 256 and belongs to a cluster of two CTAs (tcgen05 cta_group::2): each CTA stages ITS 128
-// rows of the M operand (A) and ITS 128 columns of the N operand (B); the leader CTA issues M = 256, K = 8 MMAs whose
+// rows of the M operand (A) and ITS 128 columns of the N operand (B); the leader CTA issues M = 256, N = 256 MMAs whose
 // A operand is read from both CTAs' TMEM and whose B operand is read from both CTAs' shared memory; each CTA's TMEM
 // receives its 128 accumulator rows.
 //
@@ -16,31 +16,38 @@
 //   rows  :  D = sum_k [A1 | A2][row, k] B[k, col]   (pass 2: A1 = V, B = W; Vb: A1 = V, A2 = Xb, B = [rL Binv; -W^T])
 //            A lands K-major: TMA box {16 floats, 128 rows} with SWIZZLE_64B; thread m reads its row (4 x 128 bit).
 //
-// Why A lives in TMEM.  With both operands in shared memory a 16-row stage costs, per CTA, 48 KB of MMA operand
-// reads + 32 KB of converter traffic + 16 KB of TMA writes = 848 shared-memory wavefronts against 768 tensor-pipe
-// cycles: the kernel was shared-memory-bandwidth bound (measured: 1114 cycles per stage, tensor pipe 70 % active).
-// A from TMEM removes its 24 KB of operand reads and the 8 KB lo-plane store: 512 wavefronts per stage.
+// The three terms per 16-row stage (hardware facts measured on B200, experiments/tc/exp1_gram.cu: kind::tf32
+// TRUNCATES fp32 operands, and the TMEM accumulator is rounded toward zero after every MMA):
+//   hi.hi  : two K = 8 kind::tf32 MMAs on the RAW fp32 data (the hardware truncation is the split): A from TMEM,
+//            B = the TMA tile as it landed;
+//   a.lo(b), lo(a).b : lo(x) = x - trunc_tf32(x) is exact in fp32 and has <= 13 significant bits, the other factor
+//            needs only ~11 bits, so each correction term is ONE K = 16 kind::f16 MMA on fp16 operands
+//            (x 2^-6) and (lo(x) 2^6) -- the powers of two keep both factors inside fp16's normal range for
+//            magnitudes from ~4e-3 to ~4e6 and cancel in the product; smaller entries lose relative, not absolute,
+//            precision in the CORRECTION terms only.  Half the tensor-pipe time of two tf32 MMAs, and more accurate
+//            than tf32 correction terms (fp16 rounds a to nearest where tf32 truncates it): G, C against fp64
+//            1.2-1.4e-7 of max|G| (the exact-fp32 SIMT engine: 0.9-2.5e-7).
+//   Accumulation in TMEM is limited to WINDOWS of 4 stages (64 k-rows); inside a window ALL correction terms are
+//   issued first, into the still-small accumulator, the hi.hi terms last (a correction term added to a large
+//   accumulator is truncated at the accumulator's ulp: measured 1.5e-6 with 2-stage groups in an 8-stage window).
+//   Finished windows are added in fp32 registers (round-to-nearest) by the drain warps.
 //
-// Numerics (measured on B200, experiments/tc/exp1_gram.cu): kind::tf32 TRUNCATES fp32 operands and the TMEM
-// accumulator is rounded toward zero after every MMA.  Hence
-//   * the raw fp32 value is the hi operand as it stands (the hardware truncation is the split); the converter warps
-//     only add lo = rn_tf32(a - trunc_tf32(a));
-//   * accumulation in TMEM is limited to WINDOWS of 4 stages (64 k-rows); inside a window the MMAs go out in groups
-//     of 2 stages, cross terms (hi.lo, lo.hi) first, hi.hi last, so the small terms are added while the accumulator
-//     is small; finished windows are added in fp32 registers (round-to-nearest) by the drain warps.
-//
-// TMEM map (512 columns): [0, 256) ONE accumulator tile, used as two independent 128-column halves whose windows are
-// staggered by half a window: while the drain warps empty one half the tensor pipe works on the other, which gives
-// the overlap of a double-buffered accumulator in half the columns (N = 128 MMAs cost nothing extra once A comes from
-// TMEM: B is not re-read).  [256, 512) ring of 8 A slots: 16 columns hi + 16 columns lo per 16-row stage.
+// Why A lives in TMEM.  With both operands in shared memory a 16-row stage cost, per CTA, 48 KB of MMA operand reads
+// + 32 KB of converter traffic + 16 KB of TMA writes = 848 shared-memory wavefronts against 768 tensor-pipe cycles:
+// the first pair kernel was shared-memory-bandwidth bound.  Now: 16 KB of B reads + 24 KB converter + 16 KB TMA.
+// TMEM map (512 columns): [0, 256) the accumulator tile; [256, 512) ring of 8 A slots: 16 columns raw fp32 (hi) +
+// 8 columns fp16 pairs (a 2^-6) + 8 columns fp16 pairs (lo 2^6) per stage.
+// (Measured and dropped: two staggered 128-column half accumulators -- an N = 128 MMA with A from TMEM takes ~117
+//  cycles, not 64; separate rings for the raw A and B tiles; L2 prefetch of later stages -- 30 % SLOWER: the kernel
+//  is sensitive to the TMA / L2 request rate, which is what a cluster-multicast of the shared operand would relieve.)
 //
 // Warp roles per CTA (512 threads, setmaxnreg re-balanced): warp 0 TMA producer (own halves), warp 1 MMA issuer
 // (leader CTA only) + TMEM owner, warps 4-7 converters (thread = A row = TMEM lane), warps 8-15 drain / epilogue.
-// Rings: raw tiles (TMA -> converter -> MMA, 16 KB: A raw + B raw = B hi) and lo slots (B lo plane in shared memory +
-// the A slot in TMEM; converter -> MMA).  Barriers: full[s] (local TMA -> local converters), conv[s] (converters of
-// BOTH CTAs -> leader), empty[s], lo_empty[s] and tfull[h] (MMA commit, multicast to both CTAs), tempty[h] (drain
-// warps of both CTAs -> leader).  Remote arrives use the default .release.cta semantics on purpose (.release.cluster
-// compiles to MEMBAR.ALL.GPU per arrive).
+// Rings: raw tiles (TMA -> converter -> MMA, 16 KB: A raw + B raw = B hi) and lo slots (the two fp16 planes of B in
+// shared memory + the A slot in TMEM; converter -> MMA).  Barriers: full[s] (local TMA -> local converters), conv[s]
+// (converters of BOTH CTAs -> leader), empty[s], lo_empty[s] and tfull (MMA commit, multicast to both CTAs), tempty
+// (drain warps of both CTAs -> leader).  Remote arrives use the default .release.cta semantics on purpose
+// (.release.cluster compiles to MEMBAR.ALL.GPU per arrive).
 // Pass 1 is persistent over (tile, k-split) units with a deterministic split-K: every unit writes its own partial
 // tile, tc_reduce_kernel sums them in a fixed order (fp64) and tc_mirror_kernel fills the upper triangle of G.
 #include <stdlib.h>
@@ -75,6 +82,9 @@ constexpr int kWinGroups = GPP_TC_WINGROUPS;   // groups per accumulation window
 constexpr int kABytes = HM * TBK * 4, kBBytes = HN * TBK * 4, kRawBytes = kABytes + kBBytes;   // 8 K + 8 K
 constexpr int kTcThreads = 512;
 constexpr int kSmemBytes = kRaw * kRawBytes + kLo * kBBytes + 1024 /*align*/ + 512 /*barriers*/;
+#ifndef GPP_TC_PREFETCH
+#define GPP_TC_PREFETCH 0   // pass 1: L2 prefetch distance in stages (0 = off)
+#endif
 #ifndef GPP_TC_F16X
 #define GPP_TC_F16X 1    // 1: correction terms (hi.lo, lo.hi) as ONE K = 16 fp16 MMA each; 0: as two K = 8 tf32 MMAs each
 #endif
@@ -419,6 +429,15 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
 #pragma unroll
           for (int g = 0; g < HN / 32; ++g)
             tma_load_2d(dst + kABytes + g * (TBK * 128), mb, bcol + g * 32, row, &sm->full[s]);
+#if GPP_TC_PREFETCH > 0
+          if (st + GPP_TC_PREFETCH < nst) {   // pull the tiles of a later stage into L2 (costs no shared memory)
+            const int prow = row + GPP_TC_PREFETCH * TBK;
+#pragma unroll
+            for (int g = 0; g < HM / 32; ++g) tma_prefetch_2d(&tmV, acol + g * 32, prow);
+#pragma unroll
+            for (int g = 0; g < HN / 32; ++g) tma_prefetch_2d(mb, bcol + g * 32, prow);
+          }
+#endif
         }
       }
       PROF_STORE(0);

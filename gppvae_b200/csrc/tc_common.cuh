@@ -63,6 +63,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, int
       : "memory");
 }
 
+// L2 prefetch of a 2-D tile (no shared-memory destination, no barrier): turns the DRAM latency of a later tma_load_2d of
+// the same box into an L2 hit.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(x), "r"(y)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ TMEM
 // One full warp allocates `ncols` (power of two >= 32) columns and publishes the base address in smem.
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

@@ -63,7 +63,8 @@ enum gpp_scalar_slot {
 
 int gpp_version(void);
 const char* gpp_last_error(void);
-/* Which GEMM engine the library was built with: "tcgen05-3xtf32" or "simt-fp32". */
+/* Which GEMM engine the library was built with: "tcgen05-tf32+2xf16" (3-term split: TF32 main term + two fp16
+ * correction terms) or "simt-fp32". */
 const char* gpp_gemm_engine(void);
 /* Number of kernels this library has launched in the process so far (bench.py reports the delta). */
 uint64_t gpp_launch_count(void);
