@@ -21,12 +21,14 @@
 //   hi.hi  : two K = 8 kind::tf32 MMAs on the RAW fp32 data (the hardware truncation is the split): A from TMEM,
 //            B = the TMA tile as it landed;
 //   a.lo(b), lo(a).b : lo(x) = x - trunc_tf32(x) is exact in fp32 and has <= 13 significant bits, the other factor
-//            needs only ~11 bits, so each correction term is ONE K = 16 kind::f16 MMA on fp16 operands
-//            (x 2^-6) and (lo(x) 2^6) -- the powers of two keep both factors inside fp16's normal range for
-//            magnitudes from ~4e-3 to ~4e6 and cancel in the product; smaller entries lose relative, not absolute,
-//            precision in the CORRECTION terms only.  Half the tensor-pipe time of two tf32 MMAs, and more accurate
-//            than tf32 correction terms (fp16 rounds a to nearest where tf32 truncates it): G, C against fp64
-//            1.2-1.4e-7 of max|G| (the exact-fp32 SIMT engine: 0.9-2.5e-7).
+//            needs only ~11 bits, so each correction term is ONE K = 16 kind::f16 MMA on fp16 operands.  Every fp16
+//            factor is normalised by a power of two taken from its own operand's magnitude (absmax_bits_kernel, see
+//            F16Scales), which makes the scheme independent of the units of A and B; the common factor 2^g that
+//            the two terms then carry is also given to the hi.hi term (its A operand is written to TMEM as a 2^g,
+//            exact) and removed by the drain warps (exact).  Half the tensor-pipe time of two tf32 MMAs, and more
+//            accurate than tf32 correction terms (fp16 rounds a to nearest where tf32 truncates it): G, C against
+//            fp64 1.0-1.4e-7 of max|G| for V, Z scaled anywhere between 1e-6 and 3e5 (the exact-fp32 SIMT engine:
+//            0.9-2.5e-7).
 //   Accumulation in TMEM is limited to WINDOWS of 4 stages (64 k-rows); inside a window ALL correction terms are
 //   issued first, into the still-small accumulator, the hi.hi terms last (a correction term added to a large
 //   accumulator is truncated at the accumulator's ulp: measured 1.5e-6 with 2-stage groups in an 8-stage window).
@@ -97,7 +99,48 @@ constexpr int kSmemBytes = kRaw * kRawBytes + kLo * kBBytes + 1024 /*align*/ + 5
 #ifndef GPP_TC_F16_SBO
 #define GPP_TC_F16_SBO 1024
 #endif
-constexpr float kHiScale = 0.015625f, kLoScale = 64.f;   // fp16 hi factor a 2^-6, fp16 lo factor lo 2^6: product unscaled
+// Scales of the split (all exact powers of two).  With eA, eB the binary exponents of max|A|, max|B| (measured on the
+// device by absmax_bits_kernel; 0 when unknown) every fp16 factor is normalised by its own operand's magnitude,
+//   a.lo(b)  ->  (a 2^-eA) . (lo(b) 2^(11 - eB))        lo(a).b  ->  (lo(a) 2^(11 - eA)) . (b 2^-eB)
+// (lo(x) <= 2^-10 |x|, hence the extra 2^11), so all four sit around 2^-4 with maxima near 1 whatever the units of
+// A and B are.  Both terms come out scaled by 2^g, g = 11 - eA - eB; the hi.hi term is brought to the same scale by
+// writing a 2^g (exact) as its A operand, and the drain warps multiply the finished sums by 2^-g (exact).
+struct F16Scales {
+  float a32, a_hi, a_lo, b_hi, b_lo, out;
+};
+__device__ __forceinline__ int exp_of_bits(const uint32_t* p) {
+  if (!p) return 0;
+  const uint32_t b = *p;
+  if (b == 0) return 0;
+  const int e = (int)((b >> 23) & 0xFF) - 126;   // 2^(e-1) <= max|x| < 2^e
+  return e < -50 ? -50 : (e > 50 ? 50 : e);
+}
+__device__ __forceinline__ F16Scales make_scales(int eA, int eB) {
+  const int g = 11 - eA - eB;
+  F16Scales s;
+  s.a32 = exp2f((float)g);          s.out = exp2f((float)-g);
+  s.a_hi = exp2f((float)-eA);       s.a_lo = exp2f((float)(11 - eA));
+  s.b_hi = exp2f((float)-eB);       s.b_lo = exp2f((float)(11 - eB));
+  return s;
+}
+
+// out[0] = max over the matrix of the bit pattern of |x| (monotonic in |x|); out must be zeroed before the launch.
+__global__ void __launch_bounds__(256) absmax_bits_kernel(const float* __restrict__ X, int64_t ld, int64_t rows, int cols,
+                                                          uint32_t* __restrict__ out) {
+  const int c4n = cols >> 2;
+  uint32_t m = 0;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float4* row = reinterpret_cast<const float4*>(X + r * ld);
+    for (int c = threadIdx.x; c < c4n; c += blockDim.x) {
+      const float4 v = row[c];
+      m = max(m, __float_as_uint(v.x) & 0x7FFFFFFFu); m = max(m, __float_as_uint(v.y) & 0x7FFFFFFFu);
+      m = max(m, __float_as_uint(v.z) & 0x7FFFFFFFu); m = max(m, __float_as_uint(v.w) & 0x7FFFFFFFu);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
 constexpr int kAccCols = 256, kASlotCols = 32;   // TMEM: accumulator tile, then kLo A slots (16 hi + 16 lo columns)
 static_assert(kGroup < kLo && kLo <= kRaw && kAccCols + kLo * kASlotCols <= 512, "ring sizes");
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -133,6 +176,7 @@ struct Pass1Params {
   float* G; int64_t ldg;   // V^T V  (not touched when tiles_g == 0)
   float* C; int64_t ldc;   // V^T X
   const double* scal_c;    // when set: C *= scal[V0] / scal[VN]
+  const uint32_t* amax;    // device: [0] bits of max|V|, [1] bits of max|X| (fp16 scales); may be null
 };
 
 __device__ __forceinline__ void decode_tile(const Pass1Params& p, int tile, int& tm, int& tn, bool& is_c) {
@@ -206,7 +250,8 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
 // [row][16 floats], SWIZZLE_64B).
 template <bool A_MN>
 __device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint32_t tmem, uint32_t conv0_leader,
-                                              uint32_t it, unsigned long long& pw0, unsigned long long& pw1) {
+                                              uint32_t it, const F16Scales& sc, unsigned long long& pw0,
+                                              unsigned long long& pw1) {
   const int t = threadIdx.x - 128, lane = threadIdx.x & 31, wq = t >> 5;
   const int s = it % kRaw, sl = it % kLo;
   PROF_WAIT(pw0, mbar_wait(&sm->full[s], (it / kRaw) & 1));
@@ -248,16 +293,18 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint3
     const float x0 = __uint_as_float(ahi[2 * c]), x1 = __uint_as_float(ahi[2 * c + 1]);
     const float l0 = x0 - __uint_as_float(ahi[2 * c] & 0xFFFFE000u), l1 = x1 - __uint_as_float(ahi[2 * c + 1] & 0xFFFFE000u);
 #if GPP_TC_F16_PACK == 0
-    a16[c] = pack_f16x2(x0 * kHiScale, x1 * kHiScale);
-    a16[TBK / 2 + c] = pack_f16x2(l0 * kLoScale, l1 * kLoScale);
+    a16[c] = pack_f16x2(x0 * sc.a_hi, x1 * sc.a_hi);
+    a16[TBK / 2 + c] = pack_f16x2(l0 * sc.a_lo, l1 * sc.a_lo);
 #else
-    a16[c] = pack_f16x2(x1 * kHiScale, x0 * kHiScale);
-    a16[TBK / 2 + c] = pack_f16x2(l1 * kLoScale, l0 * kLoScale);
+    a16[c] = pack_f16x2(x1 * sc.a_hi, x0 * sc.a_hi);
+    a16[TBK / 2 + c] = pack_f16x2(l1 * sc.a_lo, l0 * sc.a_lo);
 #endif
   }
   PROF_WAIT(pw1, mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1));
   tcgen05_fence_after();
   const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + kAccCols + sl * kASlotCols;
+#pragma unroll
+  for (int k = 0; k < TBK; ++k) ahi[k] = __float_as_uint(__uint_as_float(ahi[k]) * sc.a32);   // after a16: exact scaling
   tmem_st_32x16(ta, ahi);
   tmem_st_32x16(ta + TBK, a16);
   // B fp16 planes (hi plane at +0, lo plane at +4 KB), each MN-major SWIZZLE_128B: 64-column group g at g * 2 KB,
@@ -269,12 +316,12 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint3
     const int chunk = 4 * bb + ((qb >> 1) ^ (kb & 3));          // logical 8-column chunk within the 64-column group
     const uint32_t dst = bplane + jj * 2048 + (kb >> 3) * 1024 + (kb & 7) * 128 + ((chunk ^ (kb & 7)) << 4) + (qb & 1) * 8;
     const float4 v = bv[i];
-    const uint32_t h0 = pack_f16x2(v.x * kHiScale, v.y * kHiScale), h1 = pack_f16x2(v.z * kHiScale, v.w * kHiScale);
+    const uint32_t h0 = pack_f16x2(v.x * sc.b_hi, v.y * sc.b_hi), h1 = pack_f16x2(v.z * sc.b_hi, v.w * sc.b_hi);
     const float lx = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
     const float ly = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
     const float lz = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
     const float lw = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    const uint32_t l0 = pack_f16x2(lx * kLoScale, ly * kLoScale), l1 = pack_f16x2(lz * kLoScale, lw * kLoScale);
+    const uint32_t l0 = pack_f16x2(lx * sc.b_lo, ly * sc.b_lo), l1 = pack_f16x2(lz * sc.b_lo, lw * sc.b_lo);
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kBBytes / 2), "r"(l0), "r"(l1) : "memory");
   }
@@ -464,13 +511,16 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
     // ======================================================= converters
     PROF_DECL;
     const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
+    const int eV = exp_of_bits(p.amax), eX = exp_of_bits(p.amax ? p.amax + 1 : nullptr);
+    const F16Scales sc_g = make_scales(eV, eV), sc_c = make_scales(eV, eX);
     uint32_t it = 0;
     for (int u = pair; u < nunits; u += npairs) {
-      const int split = u / p.tiles;
+      const int split = u / p.tiles, tile = u - split * p.tiles;
       const int64_t r0 = (int64_t)split * p.rows_per_split;
       const int64_t r1 = min(p.n, r0 + p.rows_per_split);
       const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
-      for (int st = 0; st < nst; ++st, ++it) convert_stage<true>(base, sm, tmem, conv0, it, pw0, pw1);
+      const F16Scales sc = tile < p.tiles_g ? sc_g : sc_c;
+      for (int st = 0; st < nst; ++st, ++it) convert_stage<true>(base, sm, tmem, conv0, it, sc, pw0, pw1);
     }
     if (threadIdx.x == 128) PROF_STORE(2);
   } else {
@@ -479,6 +529,8 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
     PROF_DECL;
     const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
     const int q = warp & 3, cb = (warp - 8) >> 2;
+    const int eV = exp_of_bits(p.amax), eX = exp_of_bits(p.amax ? p.amax + 1 : nullptr);
+    const float out_g = make_scales(eV, eV).out, out_c = make_scales(eV, eX).out;
     uint32_t wc = 0;
     for (int u = pair; u < nunits; u += npairs) {
       const int split = u / p.tiles, tile = u - split * p.tiles;
@@ -490,11 +542,12 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
       for (int g = 0; g < ngroups; ++g) drain_group(sm, tmem, tempty0, g, ngroups, wc, acc, pw0);
+      const float os = tile < p.tiles_g ? out_g : out_c;   // undo the common power-of-two scale of the split (exact)
       float* out = p.partial + ((size_t)tile * p.splits + split) * (size_t)(TM * TN) +
                    (size_t)(rank * HM + q * 32 + lane) * TN + cb * 128;
 #pragma unroll
       for (int i = 0; i < 128; i += 4)
-        *reinterpret_cast<float4*>(out + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+        *reinterpret_cast<float4*>(out + i) = make_float4(os * acc[i], os * acc[i + 1], os * acc[i + 2], os * acc[i + 3]);
     }
     if (threadIdx.x == 256) PROF_STORE(3);
   }
@@ -563,6 +616,7 @@ struct RowsParams {
   // contraction at the row tile's end); tri_b: B[k, col] = 0 for k < col (start it at the column tile's start).
   int batches, a_row0, a_row_step, a_k0, a_k_step, b_k0, b_k_step, b_col0, b_col_step, tri_a, tri_b;
   int64_t out_step, n_last;
+  const uint32_t* amax;   // device: [0] bits of max|A1|, [1] bits of max|B|, [2] bits of max|A2| (fp16 scales); may be null
   const float* X; int64_t ldx;
   float* out; int64_t ldo;
   const double* scal;  // mode 0: alpha = 1 / scal[VN] when set, else alpha_host
@@ -585,6 +639,13 @@ __device__ __forceinline__ RowsUnit rows_unit(const RowsParams& p, int64_t u, in
   r.k_begin = p.tri_b ? r.ct * (TN / TBK) : 0;
   r.k_end = p.tri_a ? min(nst, (int)(r.rt + 1) * (TM / TBK)) : nst;
   return r;
+}
+
+// one scale set per launch: the [A1 | A2] parts share the accumulator, hence the common scale (larger magnitude wins)
+__device__ __forceinline__ F16Scales rows_scales(const RowsParams& p) {
+  int eA = exp_of_bits(p.amax);
+  if (p.K2 > 0 && p.amax) eA = max(eA, exp_of_bits(p.amax + 2));
+  return make_scales(eA, exp_of_bits(p.amax ? p.amax + 1 : nullptr));
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
@@ -653,9 +714,10 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     PROF_DECL;
     const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
     uint32_t it = 0;
+    const F16Scales sc = rows_scales(p);
     for (int64_t u = pair; u < nunits; u += npairs) {
       const RowsUnit un = rows_unit(p, u, nst);
-      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_stage<false>(base, sm, tmem, conv0, it, pw0, pw1);
+      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_stage<false>(base, sm, tmem, conv0, it, sc, pw0, pw1);
     }
     if (threadIdx.x == 128) PROF_STORE(2);
   } else {
@@ -666,6 +728,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     uint32_t wc = 0;
     float alpha = p.alpha_host;
     if (p.mode == 0 && p.scal) alpha = (float)(1.0 / p.scal[GPP_S_VN]);
+    const float os = rows_scales(p).out;
     for (int64_t u = pair; u < nunits; u += npairs) {
       const RowsUnit un = rows_unit(p, u, nst);
       const int64_t rt = un.rt;
@@ -676,6 +739,8 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
       for (int g = 0; g < ngroups; ++g) drain_group(sm, tmem, tempty0, g, ngroups, wc, acc, pw0);
+#pragma unroll
+      for (int i = 0; i < 128; ++i) acc[i] *= os;   // undo the common power-of-two scale of the split (exact)
       // ---- epilogue for this unit: this CTA's 128 rows, this warp's 128 columns
       const int64_t row = rt * TM + rank * HM + q * 32 + lane;
       const int col0 = ct * TN + cb * 128;
@@ -774,6 +839,19 @@ int make_map_2d(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, in
   return GPP_OK;
 }
 
+// Record the bit pattern of max|X| over (a sample of) X in *slot (zeroed here); the kernels derive the fp16 scales of
+// the correction terms from it.  Large row operands are sampled (first 8192 rows): the scale only centres the fp16
+// range, it does not affect correctness.
+constexpr int64_t kAbsmaxSampleRows = 8192;
+int launch_absmax(const float* X, int64_t ld, int64_t rows, int cols, uint32_t* slot, cudaStream_t st) {
+  if (rows > kAbsmaxSampleRows) rows = kAbsmaxSampleRows;
+  if (rows <= 0 || cols < 4) return GPP_OK;
+  const int grid = (int)(rows < 592 ? rows : 592);
+  absmax_bits_kernel<<<grid, 256, 0, st>>>(X, ld, rows, cols, slot);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
 // CTA pairs that can be co-resident (persistent grid = 2 x this); B200: 148 SMs -> up to 74 pairs.
 template <typename K>
 int pair_count(K kernel) {
@@ -855,7 +933,7 @@ bool tc_pass1_supported(int64_t n, int Q, int L) { return Q >= 128 && n >= 512 &
 size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g) {
   Pass1Params p;
   pass1_geometry(n, Q, L, skip_g, p);
-  return (size_t)p.tiles * p.splits * TM * TN * sizeof(float);
+  return (size_t)p.tiles * p.splits * TM * TN * sizeof(float) + 256 /* absmax slots */;
 }
 
 // G (Q x Q, optional) = V^T V and C (Q x L) = V^T X [* v0/vn when scal_c is set]; G == nullptr skips the Gram tiles.
@@ -864,13 +942,18 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
                     cudaStream_t st) {
   Pass1Params p;
   pass1_geometry(n, Q, L, G == nullptr, p);
-  const size_t need = (size_t)p.tiles * p.splits * TM * TN * sizeof(float);
+  const size_t part_bytes = (size_t)p.tiles * p.splits * TM * TN * sizeof(float), need = part_bytes + 256;
   if (!ws || ws_bytes < need) {
     set_error("gram_vtz (tcgen05): workspace too small (%zu < %zu bytes)", ws_bytes, need);
     return GPP_ERR_WORKSPACE;
   }
   if (p.tiles == 0) return GPP_OK;
   p.partial = static_cast<float*>(ws);
+  uint32_t* amax = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + part_bytes);
+  GPP_CUDA(cudaMemsetAsync(amax, 0, 16, st));
+  GPP_TRY(launch_absmax(V, ldv, n, Q, amax, st));
+  if (L > 0) GPP_TRY(launch_absmax(X, ldx, n, L, amax + 1, st));
+  p.amax = amax;
   p.G = G; p.ldg = ldg; p.C = C; p.ldc = ldc; p.scal_c = scal_c;
   CUtensorMap tmV, tmX;
   GPP_TRY(make_map_2d(&tmV, V, n, Q, ldv, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
@@ -895,7 +978,8 @@ bool tc_rows_supported(int64_t n, int K, int ncols) { return n >= 512 && K >= 64
 size_t tc_xb_workspace_bytes(int64_t n, int L) {
   const int64_t col_tiles = ceil_div(L, TN), row_tiles = ceil_div(n, TM);
   return align_up((size_t)col_tiles * 2 * n * sizeof(float), 256) +
-         align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256) + xb_finalize_bytes();
+         align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256) + align_up(xb_finalize_bytes(), 256) +
+         256 /* absmax slots */;
 }
 
 static int launch_rows_maps(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB, int64_t n,
@@ -914,7 +998,14 @@ static int launch_rows_maps(const CUtensorMap& tmA1, const CUtensorMap& tmA2, co
 }
 
 static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, int64_t lda2, int K2, const float* B,
-                       int64_t ldb, int64_t n, int ncols, RowsParams& p, cudaStream_t st) {
+                       int64_t ldb, int64_t n, int ncols, RowsParams& p, uint32_t* amax, cudaStream_t st) {
+  if (amax) {
+    GPP_CUDA(cudaMemsetAsync(amax, 0, 16, st));
+    GPP_TRY(launch_absmax(A1, lda1, n, K1, amax, st));
+    GPP_TRY(launch_absmax(B, ldb, (int64_t)K1 + K2, ncols, amax + 1, st));
+    if (K2 > 0) GPP_TRY(launch_absmax(A2, lda2, n, K2, amax + 2, st));
+    p.amax = amax;
+  }
   CUtensorMap tmA1, tmA2, tmB;
   GPP_TRY(make_map_2d(&tmA1, A1, n, K1, lda1, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
   if (K2 > 0) GPP_TRY(make_map_2d(&tmA2, A2, n, K2, lda2, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
@@ -931,7 +1022,13 @@ static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, i
 bool tc_blockgemm_supported(int n, int K, int ncols) { return n >= 512 && K >= 64 && ncols >= 64 && encode_fn() != nullptr; }
 
 int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64_t lda, const float* Bmat, int64_t b_rows,
-                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g, cudaStream_t st) {
+                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g, uint32_t* amax,
+                        cudaStream_t st) {
+  if (amax) {   // whole matrices: the blocks of one level have similar magnitudes
+    GPP_CUDA(cudaMemsetAsync(amax, 0, 16, st));
+    GPP_TRY(launch_absmax(Amat, lda, a_rows, (int)(a_cols & ~(int64_t)3), amax, st));
+    GPP_TRY(launch_absmax(Bmat, ldb, b_rows, (int)(b_cols & ~(int64_t)3), amax + 1, st));
+  }
   CUtensorMap tmA, tmB;
   GPP_TRY(make_map_2d(&tmA, Amat, a_rows, a_cols, lda, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
   GPP_TRY(make_map_2d(&tmB, Bmat, b_rows, b_cols, ldb, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
@@ -940,7 +1037,7 @@ int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64
   p.batches = g.batches; p.n_last = g.n_last;
   p.a_row0 = g.a_row0; p.a_row_step = g.a_row_step; p.a_k0 = g.a_k0; p.a_k_step = g.a_k_step;
   p.b_k0 = g.b_k0; p.b_k_step = g.b_k_step; p.b_col0 = g.b_col0; p.b_col_step = g.b_col_step;
-  p.tri_a = g.tri_a; p.tri_b = g.tri_b; p.out_step = g.out_step;
+  p.tri_a = g.tri_a; p.tri_b = g.tri_b; p.out_step = g.out_step; p.amax = amax;
   return launch_rows_maps(tmA, tmA, tmB, g.n, g.K, 0, g.ncols, p, st);
 }
 
@@ -960,7 +1057,10 @@ int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const
     p.quad_part = static_cast<float*>(ws);
     p.xb2_part = reinterpret_cast<double*>(static_cast<char*>(ws) + align_up((size_t)col_tiles * 2 * n * sizeof(float), 256));
   }
-  GPP_TRY(launch_rows(V, ldv, Q, nullptr, 0, 0, W, ldw, n, L, p, st));
+  uint32_t* amax = nullptr;
+  if (nll)
+    amax = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + tc_xb_workspace_bytes(n, L) - 256);
+  GPP_TRY(launch_rows(V, ldv, Q, nullptr, 0, 0, W, ldw, n, L, p, amax, st));
   if (nll) {
     double* fin = p.xb2_part + align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256) / sizeof(double);
     GPP_TRY(launch_xb_finalize(p.quad_part, (int)(col_tiles * 2), n, p.xb2_part, row_tiles * col_tiles * 16, fin, scal,
@@ -969,7 +1069,7 @@ int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const
   return GPP_OK;
 }
 
-size_t tc_vb_workspace_bytes(int Q, int L) { return (size_t)(Q + L) * Q * sizeof(float); }
+size_t tc_vb_workspace_bytes(int Q, int L) { return align_up((size_t)(Q + L) * Q * sizeof(float), 256) + 256; }
 
 int launch_tc_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const float* Binv, const float* W,
                  int64_t ldw, const double* scal, int64_t n, int Q, int L, int L_true, float* Vb, int64_t ldvb, void* ws,
@@ -984,7 +1084,8 @@ int launch_tc_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, con
   GPP_LAUNCH_CHECK();
   RowsParams p{};
   p.mode = 1; p.out = Vb; p.ldo = ldvb; p.alpha_host = 1.f;
-  return launch_rows(V, ldv, Q, Xb, ldxb, L, Bstk, Q, n, Q, p, st);
+  uint32_t* amax = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + align_up((size_t)(Q + L) * Q * sizeof(float), 256));
+  return launch_rows(V, ldv, Q, Xb, ldxb, L, Bstk, Q, n, Q, p, amax, st);
 }
 
 }  // namespace gpp

@@ -49,8 +49,10 @@ struct TcBlockGemm {
   float alpha;
 };
 bool tc_blockgemm_supported(int n, int K, int ncols);
+// amax: 16 bytes of device scratch for the operands' magnitude (fp16 scales of the correction terms), or nullptr
 int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64_t lda, const float* Bmat, int64_t b_rows,
-                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g, cudaStream_t st);
+                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g, uint32_t* amax,
+                        cudaStream_t st);
 
 bool tc_rows_supported(int64_t n, int K, int ncols);
 size_t tc_xb_workspace_bytes(int64_t n, int L);

@@ -521,7 +521,7 @@ int launch_vbs(const double* scal, int64_t n_total, int Q, int L, float* vbs, cu
 // same factorisation twice per epoch, at :235 and inside :166; the caller caches this buffer).
 struct FactorLayout {
   int Qp;
-  size_t off_bm, off_linv, off_tm, off_ld, off_part, off_tn, total;
+  size_t off_bm, off_linv, off_tm, off_ld, off_part, off_amax, off_tn, total;
   size_t tn_bytes;
 };
 
@@ -535,6 +535,7 @@ static FactorLayout factor_layout(int Q) {
   f.off_tm = o;   o += qq;
   f.off_ld = o;   o += align_up((size_t)f.Qp * NB * sizeof(float), 256);   // the 64 x 64 diagonal factors
   f.off_part = o; o += align_up((size_t)kSumsqBlocks * sizeof(double), 256);
+  f.off_amax = o; o += 256;
   f.off_tn = o;
   f.tn_bytes = tn_workspace_bytes(Q, Q, Q, 0, 1);
   if (tc_pass1_supported(Q, Q, 0)) {
@@ -547,7 +548,7 @@ static FactorLayout factor_layout(int Q) {
 }
 
 struct SolveLayout {
-  size_t off_t1, off_part, off_tn, total;
+  size_t off_t1, off_part, off_amax, off_tn, total;
   size_t tn_bytes;
 };
 
@@ -556,6 +557,7 @@ static SolveLayout solve_layout(int Q, int L) {
   size_t o = 0;
   f.off_t1 = o;   o += align_up((size_t)Q * L * sizeof(float), 256);
   f.off_part = o; o += align_up((size_t)kSumsqBlocks * sizeof(double), 256);
+  f.off_amax = o; o += 256;
   f.off_tn = o;
   f.tn_bytes = tn_workspace_bytes(Q, Q, 0, L, 0);
   if (tc_pass1_supported(Q, Q, L)) {
@@ -583,6 +585,7 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
   float* Tm = reinterpret_cast<float*>(base + f.off_tm);
   double* part = reinterpret_cast<double*>(base + f.off_part);
   void* tnws = base + f.off_tn;
+  uint32_t* amax = reinterpret_cast<uint32_t*>(base + f.off_amax);
   const int Qp = f.Qp;
   const int nb = Qp / NB;
 
@@ -595,6 +598,7 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
     GPP_LAUNCH_CHECK();
   }
   GPP_CUDA(cudaMemsetAsync(Linv, 0, (size_t)Qp * Qp * sizeof(float), st));
+  GPP_CUDA(cudaMemsetAsync(Tm, 0, (size_t)Qp * Qp * sizeof(float), st));   // scratch of the triangular inverse: finite
 
   // ---- blocked Cholesky with look-ahead: ONE kernel per 64-wide panel (see chol_step_kernel); the diagonal factors
   //      are parked in Ld so that no CTA reads a block another one rewrites
@@ -629,13 +633,13 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
       g.a_row0 = b; g.a_row_step = 2 * b; g.a_k0 = 0; g.a_k_step = 2 * b;       // C block of Lc: rows p0 + b, cols p0
       g.b_k0 = 0; g.b_k_step = 2 * b; g.b_col0 = 0; g.b_col_step = 2 * b;       // Ai: rows p0, cols p0
       g.tri_b = 1; g.alpha = 1.f;
-      GPP_TRY(launch_tc_blockgemm(Bm, Qp, Qp, Qp, Linv, Qp, Qp, Qp, Tm + (int64_t)b * Qp, Qp, g, st));
+      GPP_TRY(launch_tc_blockgemm(Bm, Qp, Qp, Qp, Linv, Qp, Qp, Qp, Tm + (int64_t)b * Qp, Qp, g, amax, st));
       TcBlockGemm x{};
       x.n = b; x.n_last = m_last; x.K = b; x.ncols = b; x.batches = npairs; x.out_step = pair_stride;
       x.a_row0 = b; x.a_row_step = 2 * b; x.a_k0 = b; x.a_k_step = 2 * b;       // Di: rows p0 + b, cols p0 + b
       x.b_k0 = b; x.b_k_step = 2 * b; x.b_col0 = 0; x.b_col_step = 2 * b;       // T: rows p0 + b, cols p0
       x.tri_a = 1; x.alpha = -1.f;
-      GPP_TRY(launch_tc_blockgemm(Linv, Qp, Qp, Qp, Tm, Qp, Qp, Qp, Linv + (int64_t)b * Qp, Qp, x, st));
+      GPP_TRY(launch_tc_blockgemm(Linv, Qp, Qp, Qp, Tm, Qp, Qp, Qp, Linv + (int64_t)b * Qp, Qp, x, amax, st));
       continue;
     }
     GemmParams t{};
@@ -693,7 +697,7 @@ int launch_solve_w(const float* C, int64_t ldc, int Q, int L, int L_true, int64_
     // tensor cores (3xTF32): T1 = Linv . C as a row GEMM, W = (v0/vn) Linv^T T1 as a transposed-A GEMM
     TcBlockGemm g{};
     g.n = Q; g.n_last = Q; g.K = Q; g.ncols = L; g.batches = 1; g.tri_a = 1; g.alpha = 1.f;
-    GPP_TRY(launch_tc_blockgemm(Linv, Q, Q, Qp, C, Q, L, ldc, T1, L, g, st));
+    GPP_TRY(launch_tc_blockgemm(Linv, Q, Q, Qp, C, Q, L, ldc, T1, L, g, reinterpret_cast<uint32_t*>(base + sl.off_amax), st));
     GPP_TRY(launch_tc_pass1(Linv, Qp, T1, L, Q, Q, L, nullptr, 0, W, ldw, scal, tnws, sl.tn_bytes, st));
   } else {
     GemmParams g{};

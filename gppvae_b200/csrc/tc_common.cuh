@@ -252,7 +252,7 @@ __device__ __forceinline__ void umma_f16_pair_ts(uint32_t tmem_d, uint32_t tmem_
 // {lo16 = fp16(a), hi16 = fp16(b)} (round to nearest)
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
   uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // overflow clamps, never inf
   return r;
 }
 

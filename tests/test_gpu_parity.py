@@ -423,3 +423,19 @@ def test_qspace_large_against_fp64(dev, Q, L, r):
     W, _ = ops.solve_w(fac, GC[:, Q:], Q + Lp, Lp, L, n)
     print(f"   W err {rel_err(W[:, :L].cpu(), W64.cpu()):.2e}")
     assert rel_err(W[:, :L].cpu(), W64.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("sv,sz", [(1.0, 1.0), (1e-4, 1e3), (1e3, 1e-5), (1e-6, 1e-6), (3e5, 2e4)])
+def test_tensor_core_pass1_scale_robustness(dev, sv, sz):
+    """The correction terms of the split run in fp16; their power-of-two scales are derived on the device from the
+    operands' magnitudes, so fp32-level accuracy must not depend on the units of V and Z."""
+    from gppvae_b200 import ops
+    n, Q, L = 6000, 512, 128
+    torch.manual_seed(7)
+    V = torch.randn(n, Q, device=dev) * sv
+    X = torch.randn(n, L, device=dev) * sz
+    ref = V.double().t() @ torch.cat([V.double(), X.double()], 1)
+    GC = ops.gram_vtz(V, Q, X, L, n, Q, L)
+    eg, ec = rel_err(GC[:, :Q].cpu(), ref[:, :Q].cpu()), rel_err(GC[:, Q:].cpu(), ref[:, Q:].cpu())
+    print(f"[pass1 scales V*{sv:g} Z*{sz:g}] G err {eg:.2e}  C err {ec:.2e}")
+    assert eg < 1e-6 and ec < 1e-6
