@@ -844,6 +844,7 @@ int make_map_2d(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, in
 // range, it does not affect correctness.
 constexpr int64_t kAbsmaxSampleRows = 8192;
 int launch_absmax(const float* X, int64_t ld, int64_t rows, int cols, uint32_t* slot, cudaStream_t st) {
+  GPP_CUDA(cudaMemsetAsync(slot, 0, 4, st));
   if (rows > kAbsmaxSampleRows) rows = kAbsmaxSampleRows;
   if (rows <= 0 || cols < 4) return GPP_OK;
   const int grid = (int)(rows < 592 ? rows : 592);
@@ -928,6 +929,10 @@ extern "C" int gpp_debug_prof(unsigned long long* out /* [512][16] */) {
 }
 #endif
 
+int tc_absmax(const float* X, int64_t ld, int64_t rows, int cols, uint32_t* slot, cudaStream_t st) {
+  return launch_absmax(X, ld, rows, cols, slot, st);
+}
+
 bool tc_pass1_supported(int64_t n, int Q, int L) { return Q >= 128 && n >= 512 && encode_fn() != nullptr; }
 
 size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g) {
@@ -950,7 +955,6 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
   if (p.tiles == 0) return GPP_OK;
   p.partial = static_cast<float*>(ws);
   uint32_t* amax = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + part_bytes);
-  GPP_CUDA(cudaMemsetAsync(amax, 0, 16, st));
   GPP_TRY(launch_absmax(V, ldv, n, Q, amax, st));
   if (L > 0) GPP_TRY(launch_absmax(X, ldx, n, L, amax + 1, st));
   p.amax = amax;
@@ -1000,7 +1004,6 @@ static int launch_rows_maps(const CUtensorMap& tmA1, const CUtensorMap& tmA2, co
 static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, int64_t lda2, int K2, const float* B,
                        int64_t ldb, int64_t n, int ncols, RowsParams& p, uint32_t* amax, cudaStream_t st) {
   if (amax) {
-    GPP_CUDA(cudaMemsetAsync(amax, 0, 16, st));
     GPP_TRY(launch_absmax(A1, lda1, n, K1, amax, st));
     GPP_TRY(launch_absmax(B, ldb, (int64_t)K1 + K2, ncols, amax + 1, st));
     if (K2 > 0) GPP_TRY(launch_absmax(A2, lda2, n, K2, amax + 2, st));
@@ -1022,13 +1025,8 @@ static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, i
 bool tc_blockgemm_supported(int n, int K, int ncols) { return n >= 512 && K >= 64 && ncols >= 64 && encode_fn() != nullptr; }
 
 int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64_t lda, const float* Bmat, int64_t b_rows,
-                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g, uint32_t* amax,
-                        cudaStream_t st) {
-  if (amax) {   // whole matrices: the blocks of one level have similar magnitudes
-    GPP_CUDA(cudaMemsetAsync(amax, 0, 16, st));
-    GPP_TRY(launch_absmax(Amat, lda, a_rows, (int)(a_cols & ~(int64_t)3), amax, st));
-    GPP_TRY(launch_absmax(Bmat, ldb, b_rows, (int)(b_cols & ~(int64_t)3), amax + 1, st));
-  }
+                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g,
+                        const uint32_t* amax, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   GPP_TRY(make_map_2d(&tmA, Amat, a_rows, a_cols, lda, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
   GPP_TRY(make_map_2d(&tmB, Bmat, b_rows, b_cols, ldb, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));

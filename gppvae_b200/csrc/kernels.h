@@ -49,10 +49,12 @@ struct TcBlockGemm {
   float alpha;
 };
 bool tc_blockgemm_supported(int n, int K, int ncols);
-// amax: 16 bytes of device scratch for the operands' magnitude (fp16 scales of the correction terms), or nullptr
+// amax (device, may be null): [0] bit pattern of max|A|, [1] of max|B| -- the magnitudes the fp16 scales of the
+// correction terms are derived from (tc_absmax fills one slot)
 int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64_t lda, const float* Bmat, int64_t b_rows,
-                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g, uint32_t* amax,
-                        cudaStream_t st);
+                        int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g,
+                        const uint32_t* amax, cudaStream_t st);
+int tc_absmax(const float* X, int64_t ld, int64_t rows, int cols, uint32_t* slot, cudaStream_t st);
 
 bool tc_rows_supported(int64_t n, int K, int ncols);
 size_t tc_xb_workspace_bytes(int64_t n, int L);

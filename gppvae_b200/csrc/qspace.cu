@@ -421,6 +421,17 @@ __global__ void __launch_bounds__(kPotfThreads) diag_store_kernel(const float* _
   for (int e = threadIdx.x; e < NB * NB; e += kPotfThreads) dst[(int64_t)(e >> 6) * ld + (e & 63)] = src[e];
 }
 
+// magnitude slots for the tensor-core block GEMMs (bit patterns of floats; see launch_tc_blockgemm)
+__global__ void amax_slots_kernel(uint32_t* __restrict__ a, int mode) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint32_t one = 0x3F800000u;
+  if (mode == 0) {
+    a[1] = one; a[2] = one; a[3] = a[0];
+  } else {
+    a[0] = one;
+  }
+}
+
 // ------------------------------------------------------------------ reductions
 // partials[blockIdx.x] = sum over this CTA's rows of sum_{c < cols} A[r][c]^2 (fixed order).  Squares are summed in
 // fp32 over 16 elements at a time and those short sums in double (B200's fp64 pipe is slow; a 16-term fp32 sum of
@@ -620,6 +631,13 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
   diag_inv_kernel<<<nb, kPotfThreads, 0, st>>>(Ld, Linv, Qp);
   GPP_LAUNCH_CHECK();
 
+  // magnitudes for the fp16 scales of the tensor-core block GEMMs below: slot 0 = max|Lc| (measured once), slot 1 = 1
+  // (B >= I, so ||Linv||_2 <= 1); T = C . Ai inherits Lc's magnitude
+  if (Qp > 512) {   // some level runs on the tensor cores
+    GPP_TRY(tc_absmax(Bm, Qp, Qp, Qp, amax, st));
+    amax_slots_kernel<<<1, 32, 0, st>>>(amax, 0);   // {0: max|Lc|, 1: 1} for T = C . Ai, {2: 1, 3: max|Lc|} for X = -Di . T
+    GPP_LAUNCH_CHECK();
+  }
   // ---- Linv by recursive doubling: inv([[A,0],[C,D]]) = [[Ai,0],[-Di C Ai, Di]]
   for (int b = NB; b < Qp; b *= 2) {
     const int npairs = (int)ceil_div(Qp - b, 2 * b);
@@ -639,7 +657,7 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
       x.a_row0 = b; x.a_row_step = 2 * b; x.a_k0 = b; x.a_k_step = 2 * b;       // Di: rows p0 + b, cols p0 + b
       x.b_k0 = b; x.b_k_step = 2 * b; x.b_col0 = 0; x.b_col_step = 2 * b;       // T: rows p0 + b, cols p0
       x.tri_a = 1; x.alpha = -1.f;
-      GPP_TRY(launch_tc_blockgemm(Linv, Qp, Qp, Qp, Tm, Qp, Qp, Qp, Linv + (int64_t)b * Qp, Qp, x, amax, st));
+      GPP_TRY(launch_tc_blockgemm(Linv, Qp, Qp, Qp, Tm, Qp, Qp, Qp, Linv + (int64_t)b * Qp, Qp, x, amax + 2, st));
       continue;
     }
     GemmParams t{};
@@ -697,7 +715,11 @@ int launch_solve_w(const float* C, int64_t ldc, int Q, int L, int L_true, int64_
     // tensor cores (3xTF32): T1 = Linv . C as a row GEMM, W = (v0/vn) Linv^T T1 as a transposed-A GEMM
     TcBlockGemm g{};
     g.n = Q; g.n_last = Q; g.K = Q; g.ncols = L; g.batches = 1; g.tri_a = 1; g.alpha = 1.f;
-    GPP_TRY(launch_tc_blockgemm(Linv, Q, Q, Qp, C, Q, L, ldc, T1, L, g, reinterpret_cast<uint32_t*>(base + sl.off_amax), st));
+    uint32_t* amax = reinterpret_cast<uint32_t*>(base + sl.off_amax);   // {1 (Linv), max|C|}
+    GPP_TRY(tc_absmax(C, ldc, Q, L, amax + 1, st));
+    amax_slots_kernel<<<1, 32, 0, st>>>(amax, 1);
+    GPP_LAUNCH_CHECK();
+    GPP_TRY(launch_tc_blockgemm(Linv, Q, Q, Qp, C, Q, L, ldc, T1, L, g, amax, st));
     GPP_TRY(launch_tc_pass1(Linv, Qp, T1, L, Q, Q, L, nullptr, 0, W, ldw, scal, tnws, sl.tn_bytes, st));
   } else {
     GemmParams g{};
