@@ -40,8 +40,8 @@
 // TMEM map (512 columns): [0, 256) the accumulator tile; [256, 512) ring of 8 A slots: 16 columns raw fp32 (hi) +
 // 8 columns fp16 pairs (a 2^-6) + 8 columns fp16 pairs (lo 2^6) per stage.
 // (Measured and dropped: two staggered 128-column half accumulators -- an N = 128 MMA with A from TMEM takes ~117
-//  cycles, not 64; separate rings for the raw A and B tiles; L2 prefetch of later stages -- 30 % SLOWER: the kernel
-//  is sensitive to the TMA / L2 request rate, which is what a cluster-multicast of the shared operand would relieve.)
+//  cycles, not 64; separate rings for the raw A and B tiles; L2 prefetch of later stages -- 30 % SLOWER; a per-wave
+//  alignment of all producers (grid-wide counter) and k-splits from 2 k to 55 k rows -- no effect on the time.)
 //
 // Warp roles per CTA (512 threads, setmaxnreg re-balanced): warp 0 TMA producer (own halves), warp 1 MMA issuer
 // (leader CTA only) + TMEM owner, warps 4-7 converters (thread = A row = TMEM lane), warps 8-15 drain / epilogue.
@@ -84,15 +84,6 @@ constexpr int kWinGroups = GPP_TC_WINGROUPS;   // groups per accumulation window
 constexpr int kABytes = HM * TBK * 4, kBBytes = HN * TBK * 4, kRawBytes = kABytes + kBBytes;   // 8 K + 8 K
 constexpr int kTcThreads = 512;
 constexpr int kSmemBytes = kRaw * kRawBytes + kLo * kBBytes + 1024 /*align*/ + 512 /*barriers*/;
-#ifndef GPP_TC_PREFETCH
-#define GPP_TC_PREFETCH 0   // pass 1: L2 prefetch distance in stages (0 = off)
-#endif
-#ifndef GPP_TC_F16X
-#define GPP_TC_F16X 1    // 1: correction terms (hi.lo, lo.hi) as ONE K = 16 fp16 MMA each; 0: as two K = 8 tf32 MMAs each
-#endif
-#ifndef GPP_TC_F16_PACK
-#define GPP_TC_F16_PACK 0   // which half of a TMEM column holds the even k of an fp16 A pair (bring-up knob)
-#endif
 #ifndef GPP_TC_F16_LBO
 #define GPP_TC_F16_LBO 2048
 #endif
@@ -208,7 +199,7 @@ __device__ __forceinline__ TcShared* tc_prologue(uint8_t* base, uint32_t& tmem) 
       mbar_init(&sm->empty[s], 1);
     }
     for (int s = 0; s < kLo; ++s) {
-      mbar_init(&sm->conv[s], 8);     // 4 converter warps x 2 CTAs (used in the leader)
+      mbar_init(&sm->conv[s], 12);    // (4 A + 2 B converter warps) x 2 CTAs (used in the leader)
       mbar_init(&sm->lo_empty[s], 1);
     }
     for (int h = 0; h < 2; ++h) {
@@ -242,24 +233,22 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
   return v;
 }
 
-// Converter warps (threads 128..255; thread t = A row t of this CTA = TMEM lane t): wait for the raw tile of ring
-// position `it`, move A (hi = raw, lo) into the TMEM slot, write the lo plane of B next to nothing else in shared
-// memory, tell the leader.  Explicit shared-space accesses, all loads before the first store (through generic
-// pointers the compiler kept every load behind the previous store).
-// A_MN: the raw A tile is MN-major (pass 1: [k-row][32-float group], SWIZZLE_128B_BASE32B) or K-major (row GEMM:
-// [row][16 floats], SWIZZLE_64B).
+// Converter warps.  Two independent chains per stage, so that neither is as long as a tensor-pipe stage:
+//   A chain, warps 4-7 (thread t = A row t of this CTA = TMEM lane t): raw A tile -> TMEM slot: 16 columns a 2^g
+//            (hi.hi term), 8 columns fp16 pairs of the normalised a, 8 columns fp16 pairs of the normalised lo(a);
+//   B chain, warps 2-3: raw B tile -> the two fp16 planes (normalised b, normalised lo(b)) in the lo slot.
+// Explicit shared-space accesses, all loads before the first store (through generic pointers the compiler kept every
+// load behind the previous store).  A_MN: the raw A tile is MN-major (pass 1: [k-row][32-float group],
+// SWIZZLE_128B_BASE32B) or K-major (row GEMM: [row][16 floats], SWIZZLE_64B).
 template <bool A_MN>
-__device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint32_t tmem, uint32_t conv0_leader,
-                                              uint32_t it, const F16Scales& sc, unsigned long long& pw0,
-                                              unsigned long long& pw1) {
+__device__ __forceinline__ void convert_a_stage(uint8_t* base, TcShared* sm, uint32_t tmem, uint32_t conv0_leader,
+                                                uint32_t it, const F16Scales& sc, unsigned long long& pw0,
+                                                unsigned long long& pw1) {
   const int t = threadIdx.x - 128, lane = threadIdx.x & 31, wq = t >> 5;
   const int s = it % kRaw, sl = it % kLo;
   PROF_WAIT(pw0, mbar_wait(&sm->full[s], (it / kRaw) & 1));
   const uint32_t raw = smem_u32(base + s * kRawBytes);
   uint32_t ahi[TBK];
-#if !GPP_TC_F16X
-  uint32_t alo[TBK];
-#endif
   if (A_MN) {
     // element (k, m = t): group wq, k-row k, 32-byte chunk ((lane / 8) ^ (k % 4)), word lane % 8
     const uint32_t a0 = raw + wq * (TBK * 128) + (lane & 7) * 4;
@@ -276,43 +265,49 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint3
       ahi[4 * c + 2] = __float_as_uint(v.z); ahi[4 * c + 3] = __float_as_uint(v.w);
     }
   }
-#if GPP_TC_F16X
-  // B: float4 (k-row kb, 32-float group g32, 16-byte position qb) chosen so that 16 lanes cover the 64 columns of one
-  // fp16 row: conflict-free 128-bit loads here and conflict-free 64-bit stores into the fp16 planes below
-  float4 bv[4];
-  const int qb = lane & 7, bb = (lane >> 3) & 1, kpar = lane >> 4;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = wq * 4 + i, jj = m & 1, kb = 2 * (m >> 1) + kpar;
-    bv[i] = lds_f32x4(raw + kABytes + (2 * jj + bb) * (TBK * 128) + kb * 128 + qb * 16);
-  }
-  // A: hi32 = raw (tf32 hh term); fp16 pairs of a 2^-6 and of (a - trunc_tf32(a)) 2^6 for the correction terms
   uint32_t a16[TBK];
 #pragma unroll
   for (int c = 0; c < TBK / 2; ++c) {
     const float x0 = __uint_as_float(ahi[2 * c]), x1 = __uint_as_float(ahi[2 * c + 1]);
     const float l0 = x0 - __uint_as_float(ahi[2 * c] & 0xFFFFE000u), l1 = x1 - __uint_as_float(ahi[2 * c + 1] & 0xFFFFE000u);
-#if GPP_TC_F16_PACK == 0
-    a16[c] = pack_f16x2(x0 * sc.a_hi, x1 * sc.a_hi);
+    a16[c] = pack_f16x2(x0 * sc.a_hi, x1 * sc.a_hi);               // even k in the low half of the TMEM column
     a16[TBK / 2 + c] = pack_f16x2(l0 * sc.a_lo, l1 * sc.a_lo);
-#else
-    a16[c] = pack_f16x2(x1 * sc.a_hi, x0 * sc.a_hi);
-    a16[TBK / 2 + c] = pack_f16x2(l1 * sc.a_lo, l0 * sc.a_lo);
-#endif
   }
+#pragma unroll
+  for (int k = 0; k < TBK; ++k) ahi[k] = __float_as_uint(__uint_as_float(ahi[k]) * sc.a32);   // exact
   PROF_WAIT(pw1, mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1));
   tcgen05_fence_after();
   const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + kAccCols + sl * kASlotCols;
-#pragma unroll
-  for (int k = 0; k < TBK; ++k) ahi[k] = __float_as_uint(__uint_as_float(ahi[k]) * sc.a32);   // after a16: exact scaling
   tmem_st_32x16(ta, ahi);
   tmem_st_32x16(ta + TBK, a16);
-  // B fp16 planes (hi plane at +0, lo plane at +4 KB), each MN-major SWIZZLE_128B: 64-column group g at g * 2 KB,
+  tmem_wait_st();
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(conv0_leader + 8u * sl);
+}
+
+__device__ __forceinline__ void convert_b_stage(uint8_t* base, TcShared* sm, uint32_t conv0_leader, uint32_t it,
+                                                const F16Scales& sc) {
+  const int lane = threadIdx.x & 31, w2 = (threadIdx.x >> 5) - 2;
+  const int s = it % kRaw, sl = it % kLo;
+  mbar_wait(&sm->full[s], (it / kRaw) & 1);
+  // float4 (k-row kb, 32-float group 2 jj + bb, 16-byte position qb) chosen so that 16 lanes cover the 64 columns of
+  // one fp16 row: conflict-free 128-bit loads here and conflict-free 64-bit stores into the fp16 planes below
+  const uint32_t braw = smem_u32(base + s * kRawBytes) + kABytes;
+  const int qb = lane & 7, bb = (lane >> 3) & 1, kpar = lane >> 4;
+  float4 bv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = w2 * 8 + i, jj = m & 1, kb = 2 * (m >> 1) + kpar;
+    bv[i] = lds_f32x4(braw + (2 * jj + bb) * (TBK * 128) + kb * 128 + qb * 16);
+  }
+  mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1);
+  // fp16 planes (hi plane at +0, lo plane at +4 KB), each MN-major SWIZZLE_128B: 64-column group g at g * 2 KB,
   // k-row k at (k / 8) * 1 KB + (k % 8) * 128 B, 16-byte chunk ((c % 64) / 8) ^ (k % 8), element (c % 8) * 2 B
   const uint32_t bplane = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = wq * 4 + i, jj = m & 1, kb = 2 * (m >> 1) + kpar;
+  for (int i = 0; i < 8; ++i) {
+    const int m = w2 * 8 + i, jj = m & 1, kb = 2 * (m >> 1) + kpar;
     const int chunk = 4 * bb + ((qb >> 1) ^ (kb & 3));          // logical 8-column chunk within the 64-column group
     const uint32_t dst = bplane + jj * 2048 + (kb >> 3) * 1024 + (kb & 7) * 128 + ((chunk ^ (kb & 7)) << 4) + (qb & 1) * 8;
     const float4 v = bv[i];
@@ -325,27 +320,6 @@ __device__ __forceinline__ void convert_stage(uint8_t* base, TcShared* sm, uint3
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kBBytes / 2), "r"(l0), "r"(l1) : "memory");
   }
-#else
-  float4 bv[kBBytes / 16 / 128];
-#pragma unroll
-  for (int i = 0; i < kBBytes / 16 / 128; ++i) bv[i] = lds_f32x4(raw + kABytes + t * 16 + i * 2048);
-#pragma unroll
-  for (int k = 0; k < TBK; ++k) alo[k] = __float_as_uint(tf32_lo(__uint_as_float(ahi[k])));
-  PROF_WAIT(pw1, mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1));
-  tcgen05_fence_after();
-  const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + kAccCols + sl * kASlotCols;
-  tmem_st_32x16(ta, ahi);
-  tmem_st_32x16(ta + TBK, alo);
-  const uint32_t blo = smem_u32(base + kRaw * kRawBytes + sl * kBBytes) + t * 16;
-#pragma unroll
-  for (int i = 0; i < kBBytes / 16 / 128; ++i) {
-    const float4 l = make_float4(tf32_lo(bv[i].x), tf32_lo(bv[i].y), tf32_lo(bv[i].z), tf32_lo(bv[i].w));
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blo + i * 2048), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w)
-                 : "memory");
-  }
-#endif
-  tmem_wait_st();
-  tcgen05_fence_before();
   fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(conv0_leader + 8u * sl);
@@ -374,7 +348,6 @@ __device__ __forceinline__ void issue_group(uint8_t* base, TcShared* sm, uint32_
     const int sl = (it + j) % kLo;
     PROF_WAIT(pw1, mbar_wait_cluster(&sm->conv[sl], ((it + j) / kLo) & 1));
     tcgen05_fence_after();
-#if GPP_TC_F16X
     // one K = 16 fp16 MMA per correction term: (a 2^-6) . (b_lo 2^6) and (a_lo 2^6) . (b 2^-6)
     constexpr uint32_t idesc16 = umma_idesc_f16(TM, TN, false, true);
     const uint32_t b16 = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
@@ -382,19 +355,6 @@ __device__ __forceinline__ void issue_group(uint8_t* base, TcShared* sm, uint32_
     umma_f16_pair_ts(d, a16, umma_desc(b16 + kBBytes / 2, GPP_TC_F16_LBO, GPP_TC_F16_SBO, kLayoutSw128), idesc16, acc);
     umma_f16_pair_ts(d, a16 + TBK / 2, umma_desc(b16, GPP_TC_F16_LBO, GPP_TC_F16_SBO, kLayoutSw128), idesc16, 1);
     acc = 1;
-#else
-    const uint32_t b_hi = smem_u32(base + ((it + j) % kRaw) * kRawBytes) + kABytes;
-    const uint32_t b_lo = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
-    const uint32_t a_hi = tmem + kAccCols + sl * kASlotCols, a_lo = a_hi + TBK;
-#pragma unroll
-    for (int kk = 0; kk < TBK / 8; ++kk) {
-      const uint64_t dbh = umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
-      const uint64_t dbl = umma_desc(b_lo + kk * 1024, TBK * 128, 512, kLayoutSw128Base32);
-      umma_tf32_pair_ts(d, a_hi + kk * 8, dbl, idesc, acc);
-      umma_tf32_pair_ts(d, a_lo + kk * 8, dbh, idesc, 1);
-      acc = 1;
-    }
-#endif
   }
   for (int j = 0; j < gst; ++j) {   // then the hi.hi terms
     const int s = (it + j) % kRaw, sl = (it + j) % kLo;
@@ -448,8 +408,22 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
   const int nunits = p.tiles * p.splits;
 
   if (warp < 4) {
-    setmaxnreg_dec<40>();
-    if (warp == 0 && lane == 0) {
+    setmaxnreg_dec<80>();
+    if (warp >= 2) {
+      // ===================================================== B converters
+      const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
+      const int eV = exp_of_bits(p.amax), eX = exp_of_bits(p.amax ? p.amax + 1 : nullptr);
+      const F16Scales sc_g = make_scales(eV, eV), sc_c = make_scales(eV, eX);
+      uint32_t it = 0;
+      for (int u = pair; u < nunits; u += npairs) {
+        const int split = u / p.tiles, tile = u - split * p.tiles;
+        const int64_t r0 = (int64_t)split * p.rows_per_split;
+        const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+        const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
+        const F16Scales sc = tile < p.tiles_g ? sc_g : sc_c;
+        for (int st = 0; st < nst; ++st, ++it) convert_b_stage(base, sm, conv0, it, sc);
+      }
+    } else if (warp == 0 && lane == 0) {
       // ===================================================== TMA producer (this CTA's halves of A and B)
       PROF_DECL;
       tma_prefetch_desc(&tmV);
@@ -476,15 +450,6 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
 #pragma unroll
           for (int g = 0; g < HN / 32; ++g)
             tma_load_2d(dst + kABytes + g * (TBK * 128), mb, bcol + g * 32, row, &sm->full[s]);
-#if GPP_TC_PREFETCH > 0
-          if (st + GPP_TC_PREFETCH < nst) {   // pull the tiles of a later stage into L2 (costs no shared memory)
-            const int prow = row + GPP_TC_PREFETCH * TBK;
-#pragma unroll
-            for (int g = 0; g < HM / 32; ++g) tma_prefetch_2d(&tmV, acol + g * 32, prow);
-#pragma unroll
-            for (int g = 0; g < HN / 32; ++g) tma_prefetch_2d(mb, bcol + g * 32, prow);
-          }
-#endif
         }
       }
       PROF_STORE(0);
@@ -507,8 +472,8 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       PROF_STORE(1);
     }
   } else if (warp < 8) {
-    setmaxnreg_dec<96>();
-    // ======================================================= converters
+    setmaxnreg_dec<80>();
+    // ======================================================= A converters
     PROF_DECL;
     const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
     const int eV = exp_of_bits(p.amax), eX = exp_of_bits(p.amax ? p.amax + 1 : nullptr);
@@ -520,12 +485,12 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       const int64_t r1 = min(p.n, r0 + p.rows_per_split);
       const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
       const F16Scales sc = tile < p.tiles_g ? sc_g : sc_c;
-      for (int st = 0; st < nst; ++st, ++it) convert_stage<true>(base, sm, tmem, conv0, it, sc, pw0, pw1);
+      for (int st = 0; st < nst; ++st, ++it) convert_a_stage<true>(base, sm, tmem, conv0, it, sc, pw0, pw1);
     }
     if (threadIdx.x == 128) PROF_STORE(2);
   } else {
     // ======================================================= drain warps: TMEM windows -> fp32 registers -> partial tile
-    setmaxnreg_inc<184>();
+    setmaxnreg_inc<176>();
     PROF_DECL;
     const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
     const int q = warp & 3, cb = (warp - 8) >> 2;
@@ -663,8 +628,16 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int nst = nst1 + nst2;
 
   if (warp < 4) {
-    setmaxnreg_dec<40>();
-    if (warp == 0 && lane == 0) {
+    setmaxnreg_dec<80>();
+    if (warp >= 2) {
+      const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
+      const F16Scales sc = rows_scales(p);
+      uint32_t it = 0;
+      for (int64_t u = pair; u < nunits; u += npairs) {
+        const RowsUnit un = rows_unit(p, u, nst);
+        for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_b_stage(base, sm, conv0, it, sc);
+      }
+    } else if (warp == 0 && lane == 0) {
       PROF_DECL;
       tma_prefetch_desc(&tmA1);
       tma_prefetch_desc(&tmA2);
@@ -710,18 +683,18 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       PROF_STORE(1);
     }
   } else if (warp < 8) {
-    setmaxnreg_dec<96>();
+    setmaxnreg_dec<80>();
     PROF_DECL;
     const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
     uint32_t it = 0;
     const F16Scales sc = rows_scales(p);
     for (int64_t u = pair; u < nunits; u += npairs) {
       const RowsUnit un = rows_unit(p, u, nst);
-      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_stage<false>(base, sm, tmem, conv0, it, sc, pw0, pw1);
+      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_a_stage<false>(base, sm, tmem, conv0, it, sc, pw0, pw1);
     }
     if (threadIdx.x == 128) PROF_STORE(2);
   } else {
-    setmaxnreg_inc<184>();
+    setmaxnreg_inc<176>();
     PROF_DECL;
     const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
     const int q = warp & 3, cb = (warp - 8) >> 2;
@@ -1008,6 +981,11 @@ static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, i
     GPP_TRY(launch_absmax(B, ldb, (int64_t)K1 + K2, ncols, amax + 1, st));
     if (K2 > 0) GPP_TRY(launch_absmax(A2, lda2, n, K2, amax + 2, st));
     p.amax = amax;
+  p.wave_ctr = reinterpret_cast<unsigned int*>(amax + 8);
+  if (const char* e = getenv("GPP_TC_WAVE_SYNC")) {   // experiment knob: 0 switches the wave alignment off
+    if (e[0] == '0') p.wave_ctr = nullptr;
+  }
+  if (p.wave_ctr) GPP_CUDA(cudaMemsetAsync(p.wave_ctr, 0, 4, st));
   }
   CUtensorMap tmA1, tmA2, tmB;
   GPP_TRY(make_map_2d(&tmA1, A1, n, K1, lda1, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
