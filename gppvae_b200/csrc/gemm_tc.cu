@@ -981,11 +981,6 @@ static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, i
     GPP_TRY(launch_absmax(B, ldb, (int64_t)K1 + K2, ncols, amax + 1, st));
     if (K2 > 0) GPP_TRY(launch_absmax(A2, lda2, n, K2, amax + 2, st));
     p.amax = amax;
-  p.wave_ctr = reinterpret_cast<unsigned int*>(amax + 8);
-  if (const char* e = getenv("GPP_TC_WAVE_SYNC")) {   // experiment knob: 0 switches the wave alignment off
-    if (e[0] == '0') p.wave_ctr = nullptr;
-  }
-  if (p.wave_ctr) GPP_CUDA(cudaMemsetAsync(p.wave_ctr, 0, 4, st));
   }
   CUtensorMap tmA1, tmA2, tmB;
   GPP_TRY(make_map_2d(&tmA1, A1, n, K1, lda1, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
