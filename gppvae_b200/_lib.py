@@ -52,6 +52,15 @@ _SIGNATURES = {
     "gpp_atb_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "gpp_atb": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, _PF, c_int64, _PF, c_size_t,
                         c_void_p]),
+    "gpp_am": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, c_float, _PF, c_int64, c_void_p]),
+    "gpp_kr_slot_sums": (c_int, [_PF, c_int64, _PF, _PF, _PF, c_int64, c_int32, c_int32, c_int32, c_int32, _PF, c_int64,
+                                 c_void_p]),
+    "gpp_kr_assemble_gc": (c_int, [_PF, c_int64, _PF, c_int32, c_int32, c_int32, c_int32, c_int32, _PF, c_int64,
+                                   c_void_p]),
+    "gpp_kr_assemble_m": (c_int, [_PF, c_int64, _PF, c_int32, c_int32, c_int32, c_int32, _PF, c_int64, c_void_p]),
+    "gpp_kr_xb_workspace_bytes": (c_size_t, [c_int64]),
+    "gpp_kr_xb_nll": (c_int, [_PF, c_int64, _PF, c_int64, _PF, _PF, c_int64, c_int64, c_int32, c_int32, _PF, _PF,
+                              c_int64, _PF, _PF, c_size_t, c_void_p]),
     "gpp_taylor_expansion_fwd": (c_int, [_PF, c_int64, _PF, c_int64, _PF, c_int64, _PF, c_int64, c_int64, c_int32,
                                          c_int32, _PF, _PF, _PF, c_void_p]),
     "gpp_taylor_expansion_bwd": (c_int, [_PF, _PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, _PF, _PF, _PF,

@@ -81,12 +81,19 @@ extern "C" int gpp_gram_vtz_simt(const float* V, int64_t ldv, const float* X, in
                    (cudaStream_t)stream);
 }
 
-extern "C" size_t gpp_atb_workspace_bytes(int64_t n, int32_t ka, int32_t kb) { return tn_workspace_bytes(n, ka, 0, kb, 0); }
+extern "C" size_t gpp_atb_workspace_bytes(int64_t n, int32_t ka, int32_t kb) {
+  const size_t a = tn_workspace_bytes(n, ka, 0, kb, 0);
+  const size_t b = tc_pass1_supported(n, ka, kb) ? tc_pass1_workspace_bytes(n, ka, kb, true) : 0;
+  return a > b ? a : b;
+}
 
 extern "C" int gpp_atb(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int32_t ka, int32_t kb,
                        float* out, int64_t ldo, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
   GPP_REQUIRE(n >= 0 && ka > 0 && kb > 0 && ka % 4 == 0 && kb % 4 == 0, "atb: bad shape");
   GPP_REQUIRE(mat_ok(A, lda, ka) && mat_ok(B, ldb, kb) && mat_ok(out, ldo, kb), "atb: bad pointer / leading dimension");
+  if (tc_pass1_supported(n, ka, kb))   // pass 1 without the Gram tiles
+    return launch_tc_pass1(A, lda, B, ldb, n, ka, kb, nullptr, 0, out, ldo, nullptr, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
   return launch_tn(A, lda, ka, nullptr, 0, 0, B, ldb, kb, n, 0, nullptr, 0, out, ldo, nullptr, workspace,
                    workspace_bytes, (cudaStream_t)stream);
 }
@@ -161,6 +168,22 @@ extern "C" int gpp_x_minus_am(const float* X, int64_t ldx, const float* A, int64
                         (cudaStream_t)stream);
   return launch_xb(A, lda, X, ldx, M, ldm, n, k, m, nullptr, alpha, out, ldo, nullptr, nullptr, 0,
                    (cudaStream_t)stream);
+}
+
+extern "C" int gpp_am(const float* A, int64_t lda, const float* M, int64_t ldm, int64_t n, int32_t k, int32_t m,
+                      float alpha, float* out, int64_t ldo, gpp_stream_t stream) {
+  GPP_REQUIRE(n >= 0 && k > 0 && m > 0 && k % 4 == 0 && m % 4 == 0 && n < (1ll << 31), "am: bad shape");
+  GPP_REQUIRE(mat_ok(A, lda, k) && mat_ok(M, ldm, m) && mat_ok(out, ldo, m), "am: bad pointer / leading dimension");
+  if (n == 0) return GPP_OK;
+  if (tc_blockgemm_supported((int)n, k, m)) {
+    TcBlockGemm g{};
+    g.n = (int)n; g.n_last = (int)n; g.K = k; g.ncols = m; g.batches = 1; g.alpha = alpha;
+    return launch_tc_blockgemm(A, n, k, lda, M, k, m, ldm, out, ldo, g, nullptr, (cudaStream_t)stream);
+  }
+  GemmParams g{};
+  g.A = A; g.lda = lda; g.B = M; g.ldb = ldm; g.C = out; g.ldc = ldo;
+  g.M = (int)n; g.N = m; g.K = k; g.M_last = -1; g.alpha = alpha; g.beta = 0.f;
+  return launch_gemm(g, false, true, 1, (cudaStream_t)stream);
 }
 
 extern "C" int gpp_vbs(const double* scal, int64_t n_total, int32_t Q, int32_t L, float* vbs, gpp_stream_t stream) {

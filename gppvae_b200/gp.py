@@ -26,6 +26,7 @@ from torch import nn
 
 from . import ops
 from ._lib import S_QUAD, S_XB2
+from .vmod import KhatriRao
 
 
 class LowRankFactor:
@@ -52,6 +53,53 @@ class LowRankFactor:
         zeros = torch.zeros(self.n, self.Q, device=self.V.device, dtype=torch.float32)
         VB = ops.x_minus_am(zeros, self.Q, self.V, self.ldv, self.fac.Binv, self.Q, self.n, self.Q, self.Q, -1.0)
         return r * VB[:, : self.Qtrue]
+
+
+class KhatriRaoFactor:
+    """`U` / `UBi` of `GP.U_UBi_Shb` when V was given in factored form (vmod.KhatriRao): carries the factors and the
+    factorisation; `GP.solve` takes the structured route with it.  `dense()` goes through the dense handle."""
+
+    def __init__(self, kind: str, kr: KhatriRao, vs: torch.Tensor, fac: ops.Factorisation):
+        self.kind, self.kr, self.vs, self.fac = kind, kr, vs, fac
+        self.n = kr.n
+        self.shape = kr.shape
+
+    def dense(self) -> torch.Tensor:
+        Vm, ldv = ops.as_matrix(self.kr.dense(), "V")
+        if Vm.shape[1] != self.fac.Q:       # p was padded to a multiple of 4: the extra columns of V are zero
+            Vp = torch.zeros(self.n, self.fac.Q, device=Vm.device, dtype=torch.float32)
+            Vp[:, : Vm.shape[1]] = Vm
+            Vm, ldv = Vp, self.fac.Q
+        return LowRankFactor(self.kind, Vm, ldv, self.fac.Q, self.shape[1], self.vs, self.fac).dense()
+
+
+class LazyVb:
+    """`Vbs[0] = dNLL/dV` (gp.py:68-71) of a structured evaluation: an N x Q matrix nobody needs whole -- the trainer only
+    gathers minibatch rows from it (train_gppvae.py:283).  `[idx]` computes those rows, r L V[idx] B^-1 - Xb[idx] W^T."""
+
+    def __init__(self, kr: KhatriRao, Xb, fac, W, scal, Q, Lk, L):
+        self.kr, self.Xb, self.fac, self.W, self.scal, self.Q, self.Lk, self.L = kr, Xb, fac, W, scal, Q, Lk, L
+        self.shape = kr.shape
+
+    def __getitem__(self, idx) -> torch.Tensor:
+        if not torch.is_tensor(idx):
+            idx = torch.as_tensor(idx, device=self.kr.device)
+        idx = idx.to(self.kr.device).reshape(-1)
+        Vr = self.kr[idx]
+        m = Vr.shape[0]
+        Vp = torch.zeros(m, self.Q, device=Vr.device, dtype=torch.float32)
+        Vp[:, : Vr.shape[1]] = Vr
+        Xbr = self.Xb[idx].contiguous()
+        Vb = ops.vb(Vp, self.Q, Xbr, self.fac.Binv, self.W, self.scal, m, self.Q, self.Lk, self.L)
+        return Vb[:, : self.shape[1]]
+
+    def dense(self, chunk: int = 65536) -> torch.Tensor:
+        n = self.kr.n
+        out = torch.empty(n, self.shape[1], device=self.kr.device, dtype=torch.float32)
+        for a in range(0, n, chunk):
+            idx = torch.arange(a, min(n, a + chunk), device=self.kr.device)
+            out[a:a + idx.numel()] = self[idx]
+        return out
 
 
 class LazySingularValues:
@@ -192,8 +240,59 @@ class GP(nn.Module):
         self._cache.store(key, (Vm, keep_vs), GC, Q + Lk, fac)
         return fac, (GC[:, Q:] if Lk else None)
 
+    # ------------------------------------------------------------------ structured route (vmod.KhatriRao)
+    def _kr_c(self, kr: KhatriRao, Xm, ldx, Lk) -> torch.Tensor:
+        """C = V^T X (Q x Lk) through the slot sums, summed over the ranks."""
+        order, slot_start = kr.index()
+        XZ = ops.kr_slot_sums(Xm, ldx, order, slot_start, kr.xn, kr.nviews, Lk, False)
+        ST = ops.atb(kr.xn, kr.p, XZ, XZ.stride(0), kr.P, kr.p, XZ.shape[1])
+        self._all_reduce(ST)
+        return ops.kr_assemble_gc(ST, kr.wn, kr.p, Lk, False)
+
+    def _kr_factorise(self, kr: KhatriRao, vs, want_binv: bool, Xm=None, ldx=0, Lk=0, vs_origin=None):
+        """Structured pass 1 (+ all-reduce of the small ST instead of GC) and the factorisation, through the cache."""
+        tok, keep_vs = self._vs_token(vs if vs_origin is None else vs_origin)
+        key = ("kr", id(kr), tok)
+        Q = kr.p * kr.q
+        fac = self._cache.lookup(key, want_binv)
+        if fac is not None:
+            self.cache_hits += 1
+            return fac, (self._kr_c(kr, Xm, ldx, Lk) if Lk else None)
+        if not Lk:      # factorisation alone (U_UBi_Shb): the slot sums still need a right-hand side to walk
+            Xm = torch.zeros(kr.n, 4, device=kr.device, dtype=torch.float32)
+            ldx, Lx = 4, 4
+        else:
+            Lx = Lk
+        order, slot_start = kr.index()
+        self._stage("pass1:start")
+        XZ = ops.kr_slot_sums(Xm, ldx, order, slot_start, kr.xn, kr.nviews, Lx, True)
+        ST = ops.atb(kr.xn, kr.p, XZ, XZ.stride(0), kr.P, kr.p, XZ.shape[1])
+        self._stage("pass1:end")
+        self._all_reduce(ST)
+        self._stage("allreduce:end")
+        GC = ops.kr_assemble_gc(ST, kr.wn, kr.p, Lx, True)
+        fac = ops.factor(GC, Q + Lx, Q, vs, want_binv)
+        self._stage("factor:end")
+        self._cache.store(key, (kr, keep_vs), GC, Q + Lx, fac)
+        return fac, (GC[:, Q:] if Lk else None)
+
+    def _kr_solve(self, kr: KhatriRao, fac, C, Xm, ldx, Lk, L, n_total):
+        """W, the scalar block, Xb = (X - V W)/vn and nll for the rows of X, V in factored form."""
+        W, scal = ops.solve_w(fac, C, C.stride(0), Lk, L, n_total)
+        self._stage("solve:end")
+        M = ops.kr_assemble_m(W, kr.wn, kr.p, Lk)
+        Y = ops.am(kr.xn, kr.p, M, M.stride(0), kr.P, kr.p, M.shape[1])
+        Xb, nll = ops.kr_xb_nll(Xm, ldx, Y, kr.d, kr.w, kr.P, kr.nviews, Lk, scal)
+        self._stage("pass2:end")
+        return W, scal, Xb, nll
+
     def U_UBi_Shb(self, Vs: Sequence[torch.Tensor], vs: torch.Tensor, want_binv: bool = False):
         """gp.py:24-38.  Returns handles (see LowRankFactor) that `solve` accepts."""
+        if len(Vs) == 1 and isinstance(Vs[0], KhatriRao):
+            kr = Vs[0]
+            fac, _ = self._kr_factorise(kr, vs, want_binv)
+            return (KhatriRaoFactor("U", kr, vs, fac), KhatriRaoFactor("UBi", kr, vs, fac),
+                    LazySingularValues(self._cache.G, kr.p * kr.q, vs))
         Vm, ldv, Q, Qtrue = self._cat(Vs, vs)
         fac, _ = self._factorise(Vm, ldv, Q, vs, want_binv)
         U = LowRankFactor("U", Vm, ldv, Q, Qtrue, vs, fac)
@@ -205,7 +304,12 @@ class GP(nn.Module):
         Xm, ldx = ops.as_matrix(X, "X")
         n, L = X.shape
         Lk = Xm.shape[1]
-        if isinstance(U, LowRankFactor):
+        if isinstance(U, KhatriRaoFactor):
+            if n != U.n:
+                raise ValueError(f"X has {n} rows but the factorisation was built for {U.n}")
+            C = self._kr_c(U.kr, Xm, ldx, Lk)
+            _, _, Xb, _ = self._kr_solve(U.kr, U.fac, C, Xm, ldx, Lk, L, self._n_total(n, X.device))
+        elif isinstance(U, LowRankFactor):
             if n != U.n:
                 raise ValueError(f"X has {n} rows but the factorisation was built for {U.n}")
             C = ops.atb(U.V, U.ldv, Xm, ldx, n, U.Q, Lk)
@@ -225,6 +329,20 @@ class GP(nn.Module):
         """Shared body of taylor_coeff and nll: returns a dict of everything computed."""
         vs_attached = self.get_vs()
         vs = vs_attached.detach()
+        if len(Vs) == 1 and isinstance(Vs[0], KhatriRao):
+            kr = Vs[0]
+            Xm, ldx = ops.as_matrix(X, "X")
+            n, L = X.shape
+            if kr.n != n:
+                raise ValueError(f"X has {n} rows but V has {kr.n}")
+            if kr.device != Xm.device:
+                raise ValueError("X and V must be on the same device")
+            Lk = Xm.shape[1]
+            n_total = self._n_total(n, X.device)
+            fac, C = self._kr_factorise(kr, vs, want_vb, Xm, ldx, Lk, vs_origin=vs_attached)
+            W, scal, Xb, nll = self._kr_solve(kr, fac, C, Xm, ldx, Lk, L, n_total)
+            return dict(vs=vs, Vm=None, kr=kr, ldv=0, Q=kr.p * kr.q, Qtrue=kr.p_true * kr.q, n=n, L=L, Lk=Lk,
+                        n_total=n_total, fac=fac, W=W, scal=scal, Xb=Xb, nll=nll)
         Vm, ldv, Q, Qtrue = self._cat(Vs, vs)
         Xm, ldx = ops.as_matrix(X, "X")
         n, L = X.shape
@@ -253,7 +371,9 @@ class GP(nn.Module):
         if self._sharded:
             self._all_reduce(scal[S_XB2:S_QUAD + 1])
         vbs = ops.vbs_from_scal(scal, c["n_total"], Q, L)
-        if need_vb:
+        if need_vb and c["Vm"] is None:
+            Vbs = [LazyVb(c["kr"], c["Xb"], c["fac"], c["W"], scal, Q, Lk, L)]
+        elif need_vb:
             Vb = ops.vb(c["Vm"], c["ldv"], c["Xb"], c["fac"].Binv, c["W"], scal, c["n"], Q, Lk, L)
             Vbs = [Vb[:, : c["Qtrue"]] if c["Qtrue"] != Q else Vb]
             self._stage("vb:end")

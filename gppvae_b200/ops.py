@@ -202,6 +202,53 @@ def x_minus_am(X, ldx, A, lda, M, ldm, n, k, m, alpha: float) -> torch.Tensor:
     return out
 
 
+def am(A: torch.Tensor, lda: int, M: torch.Tensor, ldm: int, n: int, k: int, m: int, alpha: float = 1.0) -> torch.Tensor:
+    """out = alpha * A M  (n x m)."""
+    out = torch.empty(n, m, device=A.device, dtype=torch.float32)
+    check(_lib.load().gpp_am(_p(A), lda, _p(M), ldm, n, k, m, float(alpha), _p(out), m, _stream()), "am")
+    return out
+
+
+# ----------------------------------------------------------------------------- structured Khatri-Rao path
+def kr_slot_sums(X: torch.Tensor, ldx: int, order: torch.Tensor, slot_start: torch.Tensor, xn: torch.Tensor,
+                 nviews: int, L: int, with_x: bool) -> torch.Tensor:
+    """XZ (P x nviews (p + L)) = [cnt (x) xn | per-slot sums of X]  (with_x=False: the X part alone)."""
+    P, p = xn.shape
+    XZ = torch.empty(P, nviews * ((p if with_x else 0) + L), device=X.device, dtype=torch.float32)
+    check(_lib.load().gpp_kr_slot_sums(_p(X), ldx, _p(order), _p(slot_start), _p(xn), P, p, nviews, L, int(with_x),
+                                       _p(XZ), XZ.stride(0), _stream()), "kr_slot_sums")
+    return XZ
+
+
+def kr_assemble_gc(ST: torch.Tensor, wn: torch.Tensor, p: int, L: int, with_g: bool) -> torch.Tensor:
+    nv, q = wn.shape
+    Q = p * q
+    GC = torch.empty(Q, (Q if with_g else 0) + L, device=ST.device, dtype=torch.float32)
+    check(_lib.load().gpp_kr_assemble_gc(_p(ST), ST.stride(0), _p(wn), p, q, nv, L, int(with_g), _p(GC), GC.stride(0),
+                                         _stream()), "kr_assemble_gc")
+    return GC
+
+
+def kr_assemble_m(W: torch.Tensor, wn: torch.Tensor, p: int, L: int) -> torch.Tensor:
+    nv, q = wn.shape
+    M = torch.empty(p, nv * L, device=W.device, dtype=torch.float32)
+    check(_lib.load().gpp_kr_assemble_m(_p(W), W.stride(0), _p(wn), p, q, nv, L, _p(M), M.stride(0), _stream()),
+          "kr_assemble_m")
+    return M
+
+
+def kr_xb_nll(X: torch.Tensor, ldx: int, Y: torch.Tensor, d: torch.Tensor, w: torch.Tensor, P: int, nviews: int,
+              L: int, scal: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    n = X.shape[0]
+    Xb = torch.empty(n, L, device=X.device, dtype=torch.float32)
+    nll = torch.empty(n, 1, device=X.device, dtype=torch.float32)
+    ws = _workspace(lib.gpp_kr_xb_workspace_bytes(n), X.device)
+    check(lib.gpp_kr_xb_nll(_p(X), ldx, _p(Y), Y.stride(0), _p(d), _p(w), n, P, nviews, L, _p(scal), _p(Xb), L, _p(nll),
+                            _p(ws), ws.numel(), _stream()), "kr_xb_nll")
+    return Xb, nll
+
+
 # ----------------------------------------------------------------------------- autograd glue
 class _NormalizeRows(torch.autograd.Function):
     @staticmethod

@@ -13,6 +13,93 @@ from . import ops
 from .ops import normalize_rows  # noqa: F401  (re-exported: vmod.py:10-12)
 
 
+class KhatriRao:
+    """`V = Vmodel.forward(d, w)` held as its factors instead of as an N x (p q) matrix.
+
+    `GP.taylor_coeff`, `GP.U_UBi_Shb` / `GP.solve` and `GP.nll` accept it in place of the dense tensor and then take
+    the structured route of csrc/structured.cu: V is never written and the N-long GEMMs shrink to P-long ones.
+    It is a detached snapshot of the normalised tables (what `vm(Dt, Wt).detach()` is in train_gppvae.py:161);
+    `dense()` materialises the reference tensor, `t().mm(X)` is V^T X (train_gppvae.py:237), `[idx]` the dense rows.
+    """
+
+    def __init__(self, xn: torch.Tensor, wn: torch.Tensor, d: torch.Tensor, w: torch.Tensor):
+        ops.require_cuda_f32(xn, "xn")
+        ops.require_cuda_f32(wn, "wn")
+        self.d = ops._check_index(d, "d", xn.device)
+        self.w = ops._check_index(w, "w", xn.device)
+        if self.d.shape != self.w.shape:
+            raise ValueError("d and w must have the same length")
+        P, p = xn.shape
+        self.P, self.p_true = P, p
+        self.nviews, self.q = wn.shape
+        self.wn = wn.detach().contiguous()
+        if p % 4:      # the kernels want p % 4 == 0: zero columns of xn are zero columns of V
+            xp = torch.zeros(P, ops.round4(p), device=xn.device, dtype=torch.float32)
+            xp[:, :p] = xn.detach()
+            self.xn = xp
+        else:
+            self.xn = xn.detach().contiguous()
+        self.p = self.xn.shape[1]
+        self.n = self.d.shape[0]
+        self.shape = torch.Size((self.n, p * self.q))
+        self.device = xn.device
+        self._index = None
+
+    # -- index preparation (once per (d, w): the data set does not change between epochs) ------------------
+    def index(self):
+        """(order, slot_start): row indices sorted by slot o * nviews + v (stable) and the first position of every slot;
+        rows with an index outside its table go to a trailing dummy slot (they get NaN rows of Xb, as in the dense path)."""
+        if self._index is None:
+            nslots = self.P * self.nviews
+            bad = (self.d < 0) | (self.d >= self.P) | (self.w < 0) | (self.w >= self.nviews)
+            key = torch.where(bad, torch.full_like(self.d, nslots), self.d * self.nviews + self.w)
+            order = torch.argsort(key, stable=True)
+            counts = torch.bincount(key, minlength=nslots + 1)[:nslots]
+            slot_start = torch.zeros(nslots + 1, dtype=torch.int64, device=self.device)
+            torch.cumsum(counts, 0, out=slot_start[1:])
+            self._index = (order.contiguous(), slot_start)
+        return self._index
+
+    # -- tensor-like surface the trainer touches -----------------------------------------------------------
+    def detach(self) -> "KhatriRao":
+        return self
+
+    def dense(self) -> torch.Tensor:
+        return ops.khatri_rao_fwd(self.xn[:, : self.p_true], self.wn, self.d, self.w)
+
+    def __getitem__(self, idx) -> torch.Tensor:
+        return ops.khatri_rao_fwd(self.xn[:, : self.p_true], self.wn, self.d[idx].contiguous(), self.w[idx].contiguous())
+
+    def vtx(self, X: torch.Tensor) -> torch.Tensor:
+        """V^T X (p q x m) through the slot sums: no N-long GEMM."""
+        Xm, ldx = ops.as_matrix(X, "X")
+        if Xm.shape[0] != self.n:
+            raise ValueError(f"X has {Xm.shape[0]} rows but V has {self.n}")
+        order, slot_start = self.index()
+        Lk = Xm.shape[1]
+        XZ = ops.kr_slot_sums(Xm, ldx, order, slot_start, self.xn, self.nviews, Lk, False)
+        ST = ops.atb(self.xn, self.p, XZ, XZ.stride(0), self.P, self.p, XZ.shape[1])
+        C = ops.kr_assemble_gc(ST, self.wn, self.p, Lk, False)
+        q = self.q
+        if self.p != self.p_true:
+            C = C[: self.p_true * q]
+        return C[:, : X.shape[1]]
+
+    def t(self) -> "_KhatriRaoT":
+        return _KhatriRaoT(self)
+
+
+class _KhatriRaoT:
+    def __init__(self, kr: KhatriRao):
+        self.kr = kr
+        self.shape = torch.Size((kr.shape[1], kr.shape[0]))
+
+    def mm(self, X: torch.Tensor) -> torch.Tensor:
+        return self.kr.vtx(X)
+
+    __matmul__ = mm
+
+
 class Vmodel(nn.Module):
     def __init__(self, P: int, Q: int, p: int, q: int):
         super().__init__()
@@ -31,6 +118,12 @@ class Vmodel(nn.Module):
     def forward(self, d: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
         """V[i, j*q + k] = x()[d_i, j] * v()[w_i, k]  (vmod.py:28-35), differentiable w.r.t. x0 and v0."""
         return ops._KhatriRao.apply(self.x(), self.v(), d, w)
+
+    def lazy(self, d: torch.Tensor, w: torch.Tensor) -> KhatriRao:
+        """The same V as `forward(d, w).detach()`, kept in factored form (see KhatriRao): the epoch-level call of
+        train_gppvae.py:161 when the GP term should take the structured route."""
+        with torch.no_grad():
+            return KhatriRao(self.x(), self.v(), d, w)
 
     def _init_params(self) -> None:
         """vmod.py:37-40: objects start at e_0 (+1e-3 noise), views at the identity (+1e-3 noise)."""

@@ -152,6 +152,37 @@ size_t gpp_atb_workspace_bytes(int64_t n, int32_t ka, int32_t kb);
 int gpp_atb(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int32_t ka, int32_t kb,
             float* out, int64_t ldo, void* workspace, size_t workspace_bytes, gpp_stream_t stream);
 
+/* out = alpha * A M   A:(n x k) M:(k x m).  (Y = xn [M_0 | M_1 | ...] of the structured path below.) */
+int gpp_am(const float* A, int64_t lda, const float* M, int64_t ldm, int64_t n, int32_t k, int32_t m, float alpha,
+           float* out, int64_t ldo, gpp_stream_t stream);
+
+/* ---------------- structured Khatri-Rao path (V never materialised) ----------------
+ * V[i, j q + k] = xn[d_i, j] wn[w_i, k] (vmod.py:28-35), so V^T V, V^T X and V W (gp.py:30,42-44) factor through the
+ * (object, view) slots s = o * nviews + v:
+ *   gpp_kr_slot_sums   XZ (P x nviews (p + L)):  XZ[o, v p + j] = cnt[s] xn[o, j],  XZ[o, nviews p + v L + l] = sum of
+ *                      X[i, l] over the rows of slot s.  `order` lists the row indices sorted by slot and
+ *                      slot_start (P nviews + 1) the first position of every slot in it (both int64, device; the
+ *                      caller prepares them once per (d, w)); rows of a slot are added in that order (deterministic).
+ *   ST = xn^T XZ       (p x nviews (p + L)) with gpp_atb: S_v = ST[:, v p ..], T_v = ST[:, nviews p + v L ..]
+ *                      (row-sharded callers all-reduce ST, 8 MB at c3, instead of GC)
+ *   gpp_kr_assemble_gc GC[(j,k), (j',k')] = sum_v wn[v,k] wn[v,k'] S_v[j,j'],  GC[(j,k), Q + l] = sum_v wn[v,k] T_v[j,l]
+ *                      -- the same GC = V^T [V | X] gpp_gram_vtz produces; gpp_factor / gpp_solve_w follow unchanged
+ *   gpp_kr_assemble_m  M (p x nviews L):  M[j, v L + l] = sum_k wn[v,k] W[(j,k), l];  then Y = xn M with gpp_am
+ *   gpp_kr_xb_nll      Xb_i = (X_i - Y[d_i, w_i L ..]) / vn, nll, scal[XB2], scal[QUAD]   (the contract of gpp_xb_nll)
+ * with_x = 0 / with_g = 0: only the X part (XZ, ST are nviews L wide; GC is C alone) -- a further right-hand side on
+ * a cached factorisation.  p, p*q and L must be multiples of 4. */
+int gpp_kr_slot_sums(const float* X, int64_t ldx, const int64_t* order, const int64_t* slot_start, const float* xn,
+                     int64_t P, int32_t p, int32_t nviews, int32_t L, int32_t with_x, float* XZ, int64_t ldxz,
+                     gpp_stream_t stream);
+int gpp_kr_assemble_gc(const float* ST, int64_t ldst, const float* wn, int32_t p, int32_t q, int32_t nviews, int32_t L,
+                       int32_t with_g, float* GC, int64_t ldgc, gpp_stream_t stream);
+int gpp_kr_assemble_m(const float* W, int64_t ldw, const float* wn, int32_t p, int32_t q, int32_t nviews, int32_t L,
+                      float* M, int64_t ldm, gpp_stream_t stream);
+size_t gpp_kr_xb_workspace_bytes(int64_t n);
+int gpp_kr_xb_nll(const float* X, int64_t ldx, const float* Y, int64_t ldy, const int64_t* d, const int64_t* w,
+                  int64_t n, int64_t P, int32_t nviews, int32_t L, double* scal, float* Xb, int64_t ldxb, float* nll,
+                  void* workspace, size_t workspace_bytes, gpp_stream_t stream);
+
 /* Taylor surrogate (gp.py:127-133): out_i = Xb_i.X_i + Vb_i.V_i + <vbs, softmax(lvs)> / n      */
 int gpp_taylor_expansion_fwd(const float* X, int64_t ldx, const float* Xb, int64_t ldxb, const float* V,
                              int64_t ldv, const float* Vb, int64_t ldvb, int64_t n, int32_t L, int32_t Q,
