@@ -268,6 +268,41 @@ def run_ours(args):
         gp._cache = type(gp._cache)()      # drop the cached V / Binv before the e2e leg
         torch.cuda.empty_cache()
 
+    # ---- structured route: same inputs, same outputs, V never materialised.  Reported beside
+    #      the dense path, which stays the headline (it is the path BASELINE.json's north_star names).
+    structured = None
+    if not args.skip_structured:
+        def kr_step():
+            with torch.no_grad():
+                if gp.stage_hook is not None:
+                    gp.stage_hook("kr:start")
+                return gp.taylor_coeff(pr.Z, [vm.lazy(pr.d, pr.w)], need_vb=False)
+        gp._cache = type(gp._cache)()
+        torch.cuda.empty_cache()
+        for _ in range(3):
+            kr_step()
+        events.clear()
+        gp.stage_hook = hook
+        ms_kr, launches_kr = timed(kr_step, args.steps, 0)
+        gp.stage_hook = None
+        st_kr = {}
+        for (na, ea), (nb, eb) in zip(events[:-1], events[1:]):
+            if nb.endswith(":end"):
+                st_kr.setdefault(nb[:-4], []).append(ea.elapsed_time(eb))
+            elif na == "kr:start" and nb == "pass1:start":
+                st_kr.setdefault("index_and_tables", []).append(ea.elapsed_time(eb))
+        Xb_s, _, vbs_s, nll_s = kr_step()
+        Xb_d, _, vbs_d, nll_d = step(pr.d, pr.w, pr.Z)
+        structured = {"ms_per_step": ms_kr, "value": N / (ms_kr * 1e-3), "gpu_launches": launches_kr,
+                      "stage_ms": {k: sum(v) / len(v) for k, v in st_kr.items()},
+                      "vs_dense_route": {"xb_max_rel": float((Xb_s - Xb_d).abs().max() / Xb_d.abs().max()),
+                                         "nll_sum_rel": float(((nll_s.double().sum() - nll_d.double().sum()) /
+                                                               nll_d.double().sum()).abs())},
+                      "api": "GP.taylor_coeff(Z, [Vmodel.lazy(d, w)], need_vb=False)"}
+        del Xb_s, Xb_d, nll_s, nll_d
+        gp._cache = type(gp._cache)()
+        torch.cuda.empty_cache()
+
     # ---- end to end: inputs start in pinned host memory, results end in host memory
     hd, hw, hZ = (t.cpu().pin_memory() for t in (pr.d, pr.w, pr.Z))
     h_nll = torch.empty(n, 1).pin_memory()
@@ -360,6 +395,7 @@ def run_ours(args):
                      "whole_step_roofline_ms_at_executed_passes": t_roof_k3},
         "stage_ms": stage_ms, "nll_mean": nll_mean, "xb_sumsq": xb_sq, "vbs": vbs_host,
         "full_taylor_coeff": None if ms_full is None else {"ms_per_step": ms_full, "value": N / (ms_full * 1e-3)},
+        "structured_route": structured,
     }
     if world == 1 and not args.skip_cpu:
         line["cpu_baseline"] = cpu_reference_timing(cfg, budget_s=20.0)
@@ -378,6 +414,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg")
     ap.add_argument("--skip-full", action="store_true", help="omit the full taylor_coeff (Vb) leg")
     ap.add_argument("--skip-c-entry", action="store_true", help="omit the pure-C host-buffer leg")
+    ap.add_argument("--skip-structured", action="store_true", help="omit the structured-route leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -123,7 +123,16 @@ class Vmodel(nn.Module):
         """The same V as `forward(d, w).detach()`, kept in factored form (see KhatriRao): the epoch-level call of
         train_gppvae.py:161 when the GP term should take the structured route."""
         with torch.no_grad():
-            return KhatriRao(self.x(), self.v(), d, w)
+            kr = KhatriRao(self.x(), self.v(), d, w)
+        # the sort of the rows by (object, view) slot depends on (d, w) alone: the trainer passes the same index
+        # tensors every epoch (train_gppvae.py:123-126, 161), so keep the last one
+        key = (kr.d.data_ptr(), kr.d._version, kr.w.data_ptr(), kr.w._version, kr.n, kr.P, kr.nviews)
+        cached = getattr(self, "_lazy_index", None)
+        if cached is not None and cached[0] == key:
+            kr._index = cached[1]
+        else:
+            self._lazy_index = (key, kr.index(), (kr.d, kr.w))   # keeps d, w alive so the addresses stay theirs
+        return kr
 
     def _init_params(self) -> None:
         """vmod.py:37-40: objects start at e_0 (+1e-3 noise), views at the identity (+1e-3 noise)."""
