@@ -70,6 +70,66 @@ def vb(V, ldv, Xb, Binv, W, scal, n, Q, L, L_true):
     return (r * L_true * V.double() @ Binv.double() - Xb.double() @ W.double().t()).to(torch.float32)
 
 
+# ---- structured route (csrc/structured.cu): the same contracts as the C entries, in float64 on CPU ----------------
+def require_cuda_f32(t, name, ndim=2):
+    return None
+
+
+def _check_index(t, name, device):
+    return t.contiguous()
+
+
+def khatri_rao_fwd(xn, wn, d, w):
+    return (xn.double()[d].unsqueeze(2) * wn.double()[w].unsqueeze(1)).reshape(d.shape[0], -1).to(torch.float32)
+
+
+def kr_slot_sums(X, ldx, order, slot_start, xn, nviews, L, with_x):
+    P, p = xn.shape
+    counts = slot_start[1:] - slot_start[:-1]
+    slot_of_sorted = torch.repeat_interleave(torch.arange(P * nviews), counts)
+    rows = order[: slot_of_sorted.numel()]
+    Zs = torch.zeros(P * nviews, L, dtype=torch.float64)
+    Zs.index_add_(0, slot_of_sorted, X.double()[rows][:, :L])
+    Zs = Zs.view(P, nviews * L)
+    if not with_x:
+        return Zs.to(torch.float32)
+    Xn = (counts.view(P, nviews, 1).double() * xn.double().view(P, 1, p)).reshape(P, nviews * p)
+    return torch.cat([Xn, Zs], 1).to(torch.float32)
+
+
+def kr_assemble_gc(ST, wn, p, L, with_g):
+    nv, q = wn.shape
+    wd, ST = wn.double(), ST.double()
+    off = nv * p if with_g else 0
+    T = ST[:, off:].view(p, nv, L)
+    C = torch.einsum("vk,jvl->jkl", wd, T).reshape(p * q, L)
+    if not with_g:
+        return C.to(torch.float32)
+    S = ST[:, :off].view(p, nv, p)
+    G = torch.einsum("vk,vm,jvi->jkim", wd, wd, S).reshape(p * q, p * q)
+    return torch.cat([G, C], 1).to(torch.float32)
+
+
+def kr_assemble_m(W, wn, p, L):
+    nv, q = wn.shape
+    return torch.einsum("vk,jkl->jvl", wn.double(), W.double().view(p, q, L)).reshape(p, nv * L).to(torch.float32)
+
+
+def am(A, lda, M, ldm, n, k, m, alpha=1.0):
+    return (alpha * (A.double()[:, :k] @ M.double())).to(torch.float32)
+
+
+def kr_xb_nll(X, ldx, Y, d, w, P, nviews, L, scal):
+    Yg = Y.double().view(P, nviews, L)[d, w]
+    Xb = (X.double() - Yg) / scal[S_VN]
+    quad = (X.double() * Xb).sum(1, keepdim=True)
+    scal[S_XB2] = (Xb * Xb).sum()
+    scal[S_QUAD] = quad.sum()
+    return Xb.to(torch.float32), (0.5 * quad + scal[S_ROWCONST]).to(torch.float32)
+
+
 def install(monkeypatch):
-    for name in ("as_matrix", "gram_vtz", "atb", "factor", "solve_w", "xb_nll", "vbs_from_scal", "vb"):
+    for name in ("as_matrix", "gram_vtz", "atb", "factor", "solve_w", "xb_nll", "vbs_from_scal", "vb",
+                 "require_cuda_f32", "_check_index", "khatri_rao_fwd", "kr_slot_sums", "kr_assemble_gc", "kr_assemble_m",
+                 "am", "kr_xb_nll"):
         monkeypatch.setattr(real_ops, name, globals()[name])

@@ -130,6 +130,78 @@ def test_row_sharding_world2_gloo(tmp_path, case):
     assert r0["hits"] == r1["hits"] == 1
 
 
+def _golden_kr(g):
+    from gppvae_b200.vmod import KhatriRao
+    return KhatriRao(torch.as_tensor(g["f64_xn"], dtype=torch.float32), torch.as_tensor(g["f64_wn"], dtype=torch.float32),
+                     torch.as_tensor(g["d"]).long(), torch.as_tensor(g["w"]).long())
+
+
+@pytest.mark.parametrize("case", ["faceplace_init", "faceplace_trained"])
+def test_structured_route_host_logic_against_golden(monkeypatch, case):
+    """The structured route (vmod.KhatriRao through GP.taylor_coeff / U_UBi_Shb / solve, LazyVb, V^T X) with the fake
+    engine, against the outputs of the unmodified reference in float64: the slot index, the assembly identities of
+    csrc/structured.cu and the plumbing around them."""
+    import gppvae_b200
+    fake_engine.install(monkeypatch)
+    g = load_golden(case)
+    kr = _golden_kr(g)
+    Z = torch.as_tensor(g["Z"])
+    order, slot_start = kr.index()
+    key = kr.d * kr.nviews + kr.w
+    assert torch.equal(key[order], torch.sort(key, stable=True)[0]) and slot_start[-1] == kr.n
+    assert rel_err(kr.dense(), g["f64_V"]) < 1e-6
+    gp = gppvae_b200.GP()
+    with torch.no_grad():
+        gp.lvs.copy_(torch.as_tensor(g["lvs"]))
+    Xb, Vbs, vbs, nll = gp.taylor_coeff(Z, [kr])
+    assert rel_err(nll, g["f64_nll"]) < 1e-5 and rel_err(Xb, g["f64_Xb"]) < 1e-5 and rel_err(vbs, g["f64_vbs"]) < 1e-5
+    mb = torch.as_tensor(g["mb"]).long()
+    assert rel_err(Vbs[0][mb], g["f64_Vb"][mb.numpy()]) < 1e-4            # the gather of train_gppvae.py:283
+    assert rel_err(Vbs[0].dense(), g["f64_Vb"]) < 1e-4
+    vs = gp.get_vs()
+    U, UBi, _ = gp.U_UBi_Shb([kr], vs)
+    assert gp.cache_hits == 1
+    KiX = gp.solve(Z, U, UBi, vs)
+    assert rel_err(KiX, g["f64_KiX"]) < 1e-5
+    assert rel_err(kr.t().mm(KiX), torch.as_tensor(g["f64_V"]).t() @ KiX.double()) < 1e-5   # train_gppvae.py:237
+
+
+def _kr_shard_worker(rank, world, port, case, out):
+    import gppvae_b200
+    from gppvae_b200.vmod import KhatriRao
+    from _pytest.monkeypatch import MonkeyPatch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mpch = MonkeyPatch()
+    fake_engine.install(mpch)
+    try:
+        g = load_golden(case)
+        n = g["Z"].shape[0]
+        cut = (n * 2) // 5
+        rows = slice(0, cut) if rank == 0 else slice(cut, n)
+        kr = KhatriRao(torch.as_tensor(g["f64_xn"], dtype=torch.float32), torch.as_tensor(g["f64_wn"], dtype=torch.float32),
+                       torch.as_tensor(g["d"]).long()[rows], torch.as_tensor(g["w"]).long()[rows])
+        gp = gppvae_b200.GP().shard_rows()
+        with torch.no_grad():
+            gp.lvs.copy_(torch.as_tensor(g["lvs"]))
+        Xb, _, vbs, nll = gp.taylor_coeff(torch.as_tensor(g["Z"])[rows].contiguous(), [kr], need_vb=False)
+        torch.save(dict(Xb=Xb, vbs=vbs, nll=nll), os.path.join(out, f"k{rank}.pt"))
+    finally:
+        mpch.undo()
+        dist.destroy_process_group()
+
+
+def test_structured_row_sharding_world2_gloo(tmp_path):
+    """Row shards of the structured route: the ranks all-reduce ST (the slot GEMM) instead of GC."""
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_kr_shard_worker, args=(2, port, "faceplace_trained", str(tmp_path)), nprocs=2, join=True)
+    g = load_golden("faceplace_trained")
+    r0, r1 = torch.load(os.path.join(tmp_path, "k0.pt")), torch.load(os.path.join(tmp_path, "k1.pt"))
+    assert rel_err(torch.cat([r0["Xb"], r1["Xb"]], 0), g["f64_Xb"]) < 1e-4
+    assert rel_err(torch.cat([r0["nll"], r1["nll"]], 0), g["f64_nll"]) < 1e-4
+    assert torch.equal(r0["vbs"], r1["vbs"]) and rel_err(r0["vbs"], g["f64_vbs"]) < 1e-5
+
+
 def test_synth_generator_is_seeded_and_shardable():
     from gppvae_b200.synth import make_problem
     a = make_problem(200, 4, 5, 8, seed=3)
