@@ -40,8 +40,8 @@
 // TMEM map (512 columns): [0, 256) the accumulator tile; [256, 512) ring of 8 A slots: 16 columns raw fp32 (hi) +
 // 8 columns fp16 pairs (a 2^-6) + 8 columns fp16 pairs (lo 2^6) per stage.
 // (Measured and dropped: two staggered 128-column half accumulators -- an N = 128 MMA with A from TMEM takes ~117
-//  cycles, not 64; separate rings for the raw A and B tiles; L2 prefetch of later stages -- 30 % SLOWER; a per-wave
-//  alignment of all producers (grid-wide counter) and k-splits from 2 k to 55 k rows -- no effect on the time.)
+//  cycles, not 64; separate rings for the raw A and B tiles; L2 prefetch of later stages -- 30 % SLOWER; k-splits from
+//  2 k to 55 k rows -- no effect.  Kept: the per-wave alignment of the producers, see the producer loop of pass 1.)
 //
 // Warp roles per CTA (512 threads, setmaxnreg re-balanced): warp 0 TMA producer (own halves), warp 1 MMA issuer
 // (leader CTA only) + TMEM owner, warps 4-7 converters (thread = A row = TMEM lane), warps 8-15 drain / epilogue.
@@ -168,6 +168,7 @@ struct Pass1Params {
   float* C; int64_t ldc;   // V^T X
   const double* scal_c;    // when set: C *= scal[V0] / scal[VN]
   const uint32_t* amax;    // device: [0] bits of max|V|, [1] bits of max|X| (fp16 scales); may be null
+  unsigned int* wave_ctr;  // device, zeroed before the launch: producer-units issued so far (wave alignment); may be null
 };
 
 __device__ __forceinline__ void decode_tile(const Pass1Params& p, int tile, int& tm, int& tn, bool& is_c) {
@@ -429,7 +430,25 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       tma_prefetch_desc(&tmV);
       tma_prefetch_desc(&tmX);
       uint32_t it = 0;
+      bool wave_sync = p.wave_ctr != nullptr;
       for (int u = pair; u < nunits; u += npairs) {
+        // Wave alignment: the pairs of one wave read the same rows of V at the same time (consecutive pairs share a
+        // k-range), which is what lets L2 serve most of their loads -- but only while they stay within the L2
+        // residency window of each other, and persistent CTAs drift apart (measured at c3: L2 hit rate 47 %, 166 GB
+        // of DRAM reads per launch; aligned: 79 %, 42 GB, and 8 % less time under the power cap).  So no producer
+        // starts the loads of wave w before every producer has issued all loads of wave w - 1.  It is a hint, not a
+        // dependency: a producer that has waited 2 ms (CTAs not co-resident, e.g. another stream holds SMs) stops
+        // aligning for the rest of the launch; the rings keep the tensor cores busy while a producer waits.
+        if (wave_sync && u >= npairs) {
+          const unsigned int target = 2u * (unsigned int)min((u / npairs) * npairs, nunits);
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile unsigned int*>(p.wave_ctr) < target) {
+            if (clock64() - t0 > 4000000ll) {
+              wave_sync = false;
+              break;
+            }
+          }
+        }
         const int split = u / p.tiles, tile = u - split * p.tiles;   // consecutive pairs share a k-range (L2 reuse)
         int tm, tn;
         bool is_c;
@@ -451,6 +470,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
           for (int g = 0; g < HN / 32; ++g)
             tma_load_2d(dst + kABytes + g * (TBK * 128), mb, bcol + g * 32, row, &sm->full[s]);
         }
+        if (p.wave_ctr) atomicAdd(p.wave_ctr, 1u);
       }
       PROF_STORE(0);
     } else if (warp == 1 && lane == 0 && rank == 0) {
@@ -931,6 +951,11 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
   GPP_TRY(launch_absmax(V, ldv, n, Q, amax, st));
   if (L > 0) GPP_TRY(launch_absmax(X, ldx, n, L, amax + 1, st));
   p.amax = amax;
+  p.wave_ctr = reinterpret_cast<unsigned int*>(amax + 8);
+  if (const char* e = getenv("GPP_TC_WAVE_SYNC")) {   // experiment knob: 0 switches the wave alignment off
+    if (e[0] == '0') p.wave_ctr = nullptr;
+  }
+  if (p.wave_ctr) GPP_CUDA(cudaMemsetAsync(p.wave_ctr, 0, 4, st));
   p.G = G; p.ldg = ldg; p.C = C; p.ldc = ldc; p.scal_c = scal_c;
   CUtensorMap tmV, tmX;
   GPP_TRY(make_map_2d(&tmV, V, n, Q, ldv, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
