@@ -1,0 +1,88 @@
+"""the conv VAE restatement (stock torch) and the epoch harness of gppvae_b200/epoch.py against
+golden vectors produced by the UNMODIFIED reference classes driven through train_gppvae.py's sequence
+(tests/golden/make_golden_epoch.py; float64 reference, float32-representable inputs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, rel_err
+
+
+def _golden():
+    with np.load(os.path.join(GOLDEN_DIR, "epoch", "epoch_small.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _vae(g, dtype, device="cpu"):
+    from gppvae_b200.vae import FaceVAE
+    vae = FaceVAE(img_size=int(g["cfg_img_size"]), nf=int(g["cfg_nf"]), zdim=int(g["cfg_zdim"]), steps=int(g["cfg_steps"]))
+    sd = {k[len("init.vae."):]: torch.as_tensor(v) for k, v in g.items() if k.startswith("init.vae.")}
+    assert set(sd) == set(vae.state_dict()), "state_dict keys differ from the reference's FaceVAE"
+    vae.load_state_dict(sd)
+    return vae.to(device=device, dtype=dtype)
+
+
+def test_facevae_matches_reference_cpu():
+    """encode() of the restated FaceVAE with the reference's weights reproduces the reference's Zm, Zs (float64)."""
+    g = _golden()
+    vae = _vae(g, torch.float64).eval()
+    with torch.no_grad():
+        zm, zs = vae.encode(torch.as_tensor(g["Y"], dtype=torch.float64))
+        elbo, mse, nll, kld = vae(torch.as_tensor(g["Y"], dtype=torch.float64), torch.as_tensor(g["Eps"], dtype=torch.float64))
+    assert rel_err(zm, g["out.Zm"]) < 1e-12 and rel_err(zs, g["out.Zs"]) < 1e-12
+    assert elbo.shape == (40, 1) and torch.isfinite(elbo).all() and torch.allclose(elbo, nll + kld)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lazy", [True, False])
+def test_epoch_against_reference_sequence(lazy):
+    """eval_step + train_epoch on cuda:0 (fp32 kernels) against the reference sequence in float64: metrics, the
+    accumulated gradients of every parameter before the optimiser step, and parameters after it."""
+    import gppvae_b200
+    from gppvae_b200.epoch import eval_step, train_epoch
+    dev = torch.device("cuda:0")
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = _golden()
+        vae = _vae(g, torch.float32, dev)
+        vm = gppvae_b200.Vmodel(int(g["P"]), int(g["Q"]), int(g["p"]), int(g["Q"])).to(dev)
+        gp = gppvae_b200.GP().to(dev)
+        with torch.no_grad():
+            vm.x0.copy_(torch.as_tensor(g["init.vm.x0"])); vm.v0.copy_(torch.as_tensor(g["init.vm.v0"]))
+            gp.lvs.copy_(torch.as_tensor(g["init.gp.lvs"]))
+        Y, Yv, Eps = (torch.as_tensor(g[k]).to(dev) for k in ("Y", "Yv", "Eps"))
+        D, W, Dv, Wv = (torch.as_tensor(g[k]).to(dev) for k in ("D", "W", "Dv", "Wv"))
+        bs = int(g["bs"])
+        order = torch.as_tensor(g["order"]).to(dev)
+        batches = [order[a:a + bs] for a in range(0, order.numel(), bs)]
+        vae_opt = torch.optim.Adam(vae.parameters(), lr=2e-4)
+        gp_opt = torch.optim.Adam(list(vm.parameters()) + list(gp.parameters()), lr=1e-3)
+
+        from gppvae_b200.epoch import encode_all
+        Zm, Zs = encode_all(vae, Y, bs, dev)
+        assert rel_err(Zm.cpu(), g["out.Zm"]) < 1e-4 and rel_err(Zs.cpu(), g["out.Zs"]) < 1e-4
+        ev = eval_step(vae, vm, gp, Yv, Dv, Wv, Zm, D, W, bs=bs, lazy=lazy)
+        assert abs(ev["mse_out"] - float(g["out.mse_out"])) < 1e-4 * float(g["out.mse_out"])
+        assert abs(ev["mse_val"] - float(g["out.mse_val"])) < 1e-4 * float(g["out.mse_val"])
+
+        rv = train_epoch(vae, vm, gp, Y, D, W, vae_opt, gp_opt, bs=bs, eps=Eps, batches=batches, lazy=lazy, step=False)
+        for key in ("mse", "recon_term", "pen_term", "gp_nll", "loss"):
+            assert abs(rv[key] - float(g["out." + key])) < 2e-4 * abs(float(g["out." + key])), key
+        worst = 0.0
+        for name, prm in list(vae.named_parameters()):
+            if prm.grad is not None:
+                worst = max(worst, rel_err(prm.grad.cpu(), g["grad.vae." + name]))
+        e_x0, e_v0 = rel_err(vm.x0.grad.cpu(), g["grad.vm.x0"]), rel_err(vm.v0.grad.cpu(), g["grad.vm.v0"])
+        e_lvs = rel_err(gp.lvs.grad.cpu(), g["grad.gp.lvs"])
+        print(f"[epoch lazy={lazy}] grads vs reference (fp64): vae {worst:.2e}  x0 {e_x0:.2e}  v0 {e_v0:.2e}  lvs {e_lvs:.2e}")
+        assert worst < 2e-3 and e_x0 < 2e-3 and e_v0 < 2e-3 and e_lvs < 2e-3
+        vae_opt.step(); gp_opt.step()
+        # Adam's first step moves every weight by lr * sign(grad): compare the displacement, not the sign-fragile value
+        assert rel_err((vm.x0.detach().cpu() - torch.as_tensor(g["init.vm.x0"])),
+                       g["after.vm.x0"] - g["init.vm.x0"].astype(np.float64)) < 5e-2
+        assert rel_err(gp.lvs.detach().cpu(), g["after.gp.lvs"]) < 1e-4
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
