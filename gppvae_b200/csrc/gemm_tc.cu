@@ -600,6 +600,7 @@ struct RowsParams {
   // writes out + b out_step; the last batch has n_last (<= n) rows.  tri_a: A[row, k] = 0 for k > row (stop the
   // contraction at the row tile's end); tri_b: B[k, col] = 0 for k < col (start it at the column tile's start).
   int batches, a_row0, a_row_step, a_k0, a_k_step, b_k0, b_k_step, b_col0, b_col_step, tri_a, tri_b;
+  int lower_only;      // square output: only the tiles on and below the block diagonal (symmetric rank-k updates)
   int64_t out_step, n_last;
   const uint32_t* amax;   // device: [0] bits of max|A1|, [1] bits of max|B|, [2] bits of max|A2| (fp16 scales); may be null
   const float* X; int64_t ldx;
@@ -616,11 +617,19 @@ struct RowsUnit {
 };
 __device__ __forceinline__ RowsUnit rows_unit(const RowsParams& p, int64_t u, int nst) {
   RowsUnit r;
-  const int64_t per = p.row_tiles * p.col_tiles;
+  const int64_t per = p.lower_only ? p.row_tiles * (p.row_tiles + 1) / 2 : p.row_tiles * p.col_tiles;
   r.batch = (int)(u / per);
   const int64_t v = u - (int64_t)r.batch * per;
-  r.rt = v / p.col_tiles;
-  r.ct = (int)(v - r.rt * p.col_tiles);
+  if (p.lower_only) {
+    int64_t t = (int64_t)((sqrtf(8.f * (float)v + 1.f) - 1.f) * 0.5f);
+    while ((t + 1) * (t + 2) / 2 <= v) ++t;
+    while (t * (t + 1) / 2 > v) --t;
+    r.rt = t;
+    r.ct = (int)(v - t * (t + 1) / 2);
+  } else {
+    r.rt = v / p.col_tiles;
+    r.ct = (int)(v - r.rt * p.col_tiles);
+  }
   r.k_begin = p.tri_b ? r.ct * (TN / TBK) : 0;
   r.k_end = p.tri_a ? min(nst, (int)(r.rt + 1) * (TM / TBK)) : nst;
   return r;
@@ -643,7 +652,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   uint32_t tmem;
   TcShared* sm = tc_prologue(base, tmem);
-  const int64_t nunits = p.row_tiles * p.col_tiles * p.batches;
+  const int64_t nunits = (p.lower_only ? p.row_tiles * (p.row_tiles + 1) / 2 : p.row_tiles * p.col_tiles) * p.batches;
   const int nst1 = (p.K1 + TBK - 1) / TBK, nst2 = (p.K2 + TBK - 1) / TBK;
   const int nst = nst1 + nst2;
 
@@ -991,7 +1000,7 @@ static int launch_rows_maps(const CUtensorMap& tmA1, const CUtensorMap& tmA2, co
   if (p.n_last <= 0) p.n_last = n;
   p.col_tiles = (int)ceil_div(ncols, TN);
   p.row_tiles = ceil_div(n, TM);
-  const int64_t nunits = p.row_tiles * p.col_tiles * p.batches;
+  const int64_t nunits = (p.lower_only ? p.row_tiles * (p.row_tiles + 1) / 2 : p.row_tiles * p.col_tiles) * p.batches;
   const int pairs = (int)(nunits < rows_pairs() ? nunits : rows_pairs());
   if (pairs <= 0) return GPP_OK;
   tc_rows_kernel<<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmA1, tmA2, tmB, p);
@@ -1035,6 +1044,18 @@ int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64
   p.b_k0 = g.b_k0; p.b_k_step = g.b_k_step; p.b_col0 = g.b_col0; p.b_col_step = g.b_col_step;
   p.tri_a = g.tri_a; p.tri_b = g.tri_b; p.out_step = g.out_step; p.amax = amax;
   return launch_rows_maps(tmA, tmA, tmB, g.n, g.K, 0, g.ncols, p, st);
+}
+
+// Symmetric rank-K update of the lower block triangle, in place:  C -= A A^T  with A (n x K, ld = lda) and its transpose
+// At (K x n, ld = ldat) both given (the Cholesky's trailing update; only tiles with column tile <= row tile are touched).
+int launch_tc_syrk_sub(float* C, int64_t ldc, const float* A, int64_t lda, const float* At, int64_t ldat, int n, int K,
+                       const uint32_t* amax, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  GPP_TRY(make_map_2d(&tmA, A, n, K, lda, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
+  GPP_TRY(make_map_2d(&tmB, At, K, n, ldat, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  RowsParams p{};
+  p.mode = 0; p.X = C; p.ldx = ldc; p.out = C; p.ldo = ldc; p.alpha_host = 1.f; p.lower_only = 1; p.amax = amax;
+  return launch_rows_maps(tmA, tmA, tmB, n, K, 0, n, p, st);
 }
 
 // out = alpha (X - A M); with nll != nullptr also the NLL epilogue (quad partials -> xb_finalize).

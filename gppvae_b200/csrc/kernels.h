@@ -54,6 +54,9 @@ bool tc_blockgemm_supported(int n, int K, int ncols);
 int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64_t lda, const float* Bmat, int64_t b_rows,
                         int64_t b_cols, int64_t ldb, float* out, int64_t ldo, const TcBlockGemm& g,
                         const uint32_t* amax, cudaStream_t st);
+// C -= A A^T on the lower block triangle (C n x n in place, A n x K, At = A^T K x n); n >= 512, K >= 64
+int launch_tc_syrk_sub(float* C, int64_t ldc, const float* A, int64_t lda, const float* At, int64_t ldat, int n, int K,
+                       const uint32_t* amax, cudaStream_t st);
 int tc_absmax(const float* X, int64_t ld, int64_t rows, int cols, uint32_t* slot, cudaStream_t st);
 
 bool tc_rows_supported(int64_t n, int K, int ncols);

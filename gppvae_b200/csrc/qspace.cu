@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include <cstdlib>
 #include "kernels.h"
 
 namespace gpp {
@@ -224,8 +225,14 @@ struct StepSmem {
 };
 constexpr size_t kStepSmemBytes = sizeof(StepSmem) > sizeof(TileSmem) ? sizeof(StepSmem) : sizeof(TileSmem);
 
+constexpr int kOuterCholMinQ = 6144;   // padded Q from which the Cholesky uses 256-wide outer blocks + tensor-core updates
+
+// apply_prev: panel j - 1 has not been applied to column j and beyond yet (false for the first panel of an outer block,
+// whose columns received everything from the tensor-core update of the previous outer block).  wide_cols < 0: the wide
+// role covers the whole trailing matrix; otherwise only its first wide_cols (<= 2) 64-column blocks, all rows -- the
+// columns of the current 256-wide outer block; the rest of the matrix gets the whole outer block in one rank-256 update.
 __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __restrict__ Bm, int Qp, int j,
-                                                                 float* __restrict__ Ld) {
+                                                                 float* __restrict__ Ld, int apply_prev, int wide_cols) {
   extern __shared__ __align__(16) uint8_t step_smem[];
   const int tid = threadIdx.x;
   const int nb = Qp / NB, k0 = j * NB;
@@ -234,15 +241,22 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
     // ------------------------------------------------------------ wide role: trailing update of panel j - 1
     TileSmem& sm = *reinterpret_cast<TileSmem*>(step_smem);
     const int widx = (int)blockIdx.x - npanel;
-    int ti = (int)((sqrtf(8.f * (float)widx + 1.f) - 1.f) * 0.5f);
-    while ((ti + 1) * (ti + 2) / 2 <= widx) ++ti;
-    while (ti * (ti + 1) / 2 > widx) --ti;
-    const int tc = widx - ti * (ti + 1) / 2;
+    int ti, tc;
+    if (wide_cols < 0) {
+      ti = (int)((sqrtf(8.f * (float)widx + 1.f) - 1.f) * 0.5f);
+      while ((ti + 1) * (ti + 2) / 2 <= widx) ++ti;
+      while (ti * (ti + 1) / 2 > widx) --ti;
+      tc = widx - ti * (ti + 1) / 2;
+    } else {
+      ti = widx;
+      tc = 0;
+    }
     const int t0 = k0 + NB;
     const int r0 = t0 + ti * BM, c0 = t0 + tc * BN;
     Operand A, B;
     A.base = Bm + (int64_t)r0 * Qp + (k0 - NB); A.ld = Qp; A.mn_valid = min(BM, Qp - r0);
     B.base = Bm + (int64_t)c0 * Qp + (k0 - NB); B.ld = Qp; B.mn_valid = min(BN, Qp - c0);
+    if (wide_cols >= 0) B.mn_valid = min(B.mn_valid, wide_cols * NB);
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
       const int64_t off = (int64_t)(lr + 16 * i) * Qp + lc;
       vd[i] = *reinterpret_cast<const float4*>(D + off);
       if (b > 0) vp[i] = *reinterpret_cast<const float4*>(P + off);
-      if (j > 0) {
+      if (apply_prev) {
         vl[i] = *reinterpret_cast<const float4*>(Lj + off);
         if (b > 0) vq[i] = *reinterpret_cast<const float4*>(Lp + off);
       }
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
       const int r = lr + 16 * i;
       *reinterpret_cast<float4*>(&S.As.a[r][lc]) = vd[i];
       if (b > 0) *reinterpret_cast<float4*>(&S.Xs.a[r][lc]) = vp[i];
-      if (j > 0) {   // rank-64 update operands staged transposed: [k][row]
+      if (apply_prev) {   // rank-64 update operands staged transposed: [k][row]
         S.LsT.a[lc + 0][r] = vl[i].x; S.LsT.a[lc + 1][r] = vl[i].y; S.LsT.a[lc + 2][r] = vl[i].z; S.LsT.a[lc + 3][r] = vl[i].w;
         if (b > 0) {
           S.PsT.a[lc + 0][r] = vq[i].x; S.PsT.a[lc + 1][r] = vq[i].y; S.PsT.a[lc + 2][r] = vq[i].z; S.PsT.a[lc + 3][r] = vq[i].w;
@@ -303,7 +317,7 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
       }
     }
   }
-  if (j > 0) {
+  if (apply_prev) {
     // rank-64 update from panel j - 1:  D -= Lj Lj^T,  P -= Lp Lj^T
     __syncthreads();
     CPROF(1);
@@ -421,14 +435,29 @@ __global__ void __launch_bounds__(kPotfThreads) diag_store_kernel(const float* _
   for (int e = threadIdx.x; e < NB * NB; e += kPotfThreads) dst[(int64_t)(e >> 6) * ld + (e & 63)] = src[e];
 }
 
+// At (cols x rows, ld = ldt) = A^T for A (rows x cols, ld = lda)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ A, int64_t lda, int rows, int cols,
+                                                        float* __restrict__ At, int64_t ldt) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = ty; i < 32; i += 8)
+    tile[i][tx] = (r0 + i < rows && c0 + tx < cols) ? A[(int64_t)(r0 + i) * lda + c0 + tx] : 0.f;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols && r0 + tx < rows) At[(int64_t)(c0 + i) * ldt + r0 + tx] = tile[tx][i];
+}
+
 // magnitude slots for the tensor-core block GEMMs (bit patterns of floats; see launch_tc_blockgemm)
 __global__ void amax_slots_kernel(uint32_t* __restrict__ a, int mode) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const uint32_t one = 0x3F800000u;
   if (mode == 0) {
     a[1] = one; a[2] = one; a[3] = a[0];
-  } else {
+  } else if (mode == 1) {
     a[0] = one;
+  } else {
+    a[1] = a[0];
   }
 }
 
@@ -619,12 +648,54 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
     GPP_CUDA(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepSmemBytes));
     step_attr = true;
   }
+  // Outer blocks of kOuter panels: inside a block the panels update each other (rank-64 updates in chol_step_kernel),
+  // everything to the right of the block gets the block's kOuter panels at once, as ONE rank-256 update on the tensor
+  // cores (C -= Lp Lp^T, lower tiles).  Measured (factor_only.py): Q = 8192 10.1 -> 8.1 ms, where the SIMT trailing
+  // updates were the larger half of the stage; Q = 4096 2.40 -> 2.84 ms, where the look-ahead of the single-level scheme
+  // hides them completely behind the panel chain (64 x 23 us) and the 16 serial rank-256 updates (37-70 us each, a
+  // 256-deep contraction does not amortise the tensor-core kernel's pipeline fill and epilogue) do not.  Hence the switch.
+  constexpr int kOuter = 4;
+  const char* min_q_env = getenv("GPP_CHOL_OUTER_MIN_Q");             // tests force the outer scheme at small Q
+  const bool outer = Qp >= (min_q_env ? atoi(min_q_env) : kOuterCholMinQ);
   for (int j = 0; j < nb; ++j) {
     const int npanel = nb - j;
-    const int trail = Qp - (j + 1) * NB;
-    const int T = j > 0 ? (trail + BM - 1) / BM : 0;
-    chol_step_kernel<<<npanel + T * (T + 1) / 2, kPotfThreads, kStepSmemBytes, st>>>(Bm, Qp, j, Ld);
+    const int jj = outer ? j % kOuter : 0;
+    const int blk_end = outer ? ((j / kOuter + 1) * kOuter < nb ? (j / kOuter + 1) * kOuter : nb) : nb;   // first block after the outer block
+    const int apply_prev = outer ? (jj > 0) : (j > 0);
+    int wide_cols, wide_ctas;
+    if (!outer) {
+      const int trail = Qp - (j + 1) * NB;
+      const int T = j > 0 ? (trail + BM - 1) / BM : 0;
+      wide_cols = -1;
+      wide_ctas = T * (T + 1) / 2;
+    } else {
+      wide_cols = apply_prev ? blk_end - (j + 1) : 0;                 // column blocks j+1 .. blk_end-1 of this outer block
+      wide_ctas = wide_cols > 0 ? (Qp - (j + 1) * NB + BM - 1) / BM : 0;
+    }
+    chol_step_kernel<<<npanel + wide_ctas, kPotfThreads, kStepSmemBytes, st>>>(Bm, Qp, j, Ld, apply_prev, wide_cols);
     GPP_LAUNCH_CHECK();
+    if (outer && j + 1 == blk_end && blk_end < nb) {
+      // rank-(kOuter * 64) update of everything right of the outer block
+      const int c0 = (j / kOuter) * kOuter * NB;               // first column of the outer block
+      const int K = (blk_end * NB) - c0;
+      const int r0 = blk_end * NB, rem = Qp - r0;
+      const float* Lp = Bm + (int64_t)r0 * Qp + c0;          // rem x K panel
+      float* Cc = Bm + (int64_t)r0 * (Qp + 1);               // trailing matrix
+      if (rem >= 512) {
+        dim3 tg((unsigned)ceil_div(rem, 32), (unsigned)ceil_div(K, 32));
+        transpose_kernel<<<tg, 256, 0, st>>>(Lp, Qp, rem, K, Tm, Qp);
+        GPP_LAUNCH_CHECK();
+        GPP_TRY(tc_absmax(Lp, Qp, rem, K, amax, st));
+        amax_slots_kernel<<<1, 32, 0, st>>>(amax, 2);
+        GPP_LAUNCH_CHECK();
+        GPP_TRY(launch_tc_syrk_sub(Cc, Qp, Lp, Qp, Tm, Qp, rem, K, amax, st));
+      } else {
+        GemmParams g{};
+        g.A = Lp; g.lda = Qp; g.B = Lp; g.ldb = Qp; g.C = Cc; g.ldc = Qp;
+        g.M = rem; g.N = rem; g.K = K; g.M_last = -1; g.alpha = -1.f; g.beta = 1.f; g.lower_only = 1;
+        GPP_TRY(launch_gemm(g, false, false, 1, st));
+      }
+    }
   }
   diag_store_kernel<<<nb, kPotfThreads, 0, st>>>(Ld, Bm, Qp);
   GPP_LAUNCH_CHECK();

@@ -425,6 +425,15 @@ def test_qspace_large_against_fp64(dev, Q, L, r):
     assert rel_err(W[:, :L].cpu(), W64.cpu()) < 1e-4
 
 
+@pytest.mark.parametrize("Q,L,r", [(1600, 132, 50.0), (2048, 256, 400.0)])
+def test_qspace_outer_block_cholesky(dev, monkeypatch, Q, L, r):
+    """From Q = 6144 up the Cholesky works in 256-wide outer blocks whose trailing updates are rank-256 products on the
+    tensor cores (qspace.cu launch_factor); GPP_CHOL_OUTER_MIN_Q lowers the switch so that the scheme (tensor-core
+    updates from 512 remaining rows up, SIMT below, ragged last block) is checked where a float64 factor is cheap."""
+    monkeypatch.setenv("GPP_CHOL_OUTER_MIN_Q", "1024")
+    test_qspace_large_against_fp64(dev, Q, L, r)
+
+
 @pytest.mark.parametrize("sv,sz", [(1.0, 1.0), (1e-4, 1e3), (1e3, 1e-5), (1e-6, 1e-6), (3e5, 2e4)])
 def test_tensor_core_pass1_scale_robustness(dev, sv, sz):
     """The correction terms of the split run in fp16; their power-of-two scales are derived on the device from the
