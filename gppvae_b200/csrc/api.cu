@@ -64,7 +64,7 @@ extern "C" int gpp_gram_vtz(const float* V, int64_t ldv, const float* X, int64_t
   GPP_REQUIRE(mat_ok(GC, ldgc, (int64_t)Q + L), "gram_vtz: GC must be 16-byte aligned with ldgc >= Q + L");
   // large problems run on the tensor cores (3xTF32); tiles that cannot fill a 256 x 256 pair UMMA use the fp32 tile engine
   if (tc_pass1_supported(n, Q, L))
-    return launch_tc_pass1(V, ldv, X, ldx, n, Q, L, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes,
+    return launch_tc_pass1(V, ldv, X, ldx, n, Q, L, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes, false,
                            (cudaStream_t)stream);
   return launch_tn(V, ldv, Q, V, ldv, Q, X, ldx, L, n, 1, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes,
                    (cudaStream_t)stream);
@@ -92,7 +92,7 @@ extern "C" int gpp_atb(const float* A, int64_t lda, const float* B, int64_t ldb,
   GPP_REQUIRE(n >= 0 && ka > 0 && kb > 0 && ka % 4 == 0 && kb % 4 == 0, "atb: bad shape");
   GPP_REQUIRE(mat_ok(A, lda, ka) && mat_ok(B, ldb, kb) && mat_ok(out, ldo, kb), "atb: bad pointer / leading dimension");
   if (tc_pass1_supported(n, ka, kb))   // pass 1 without the Gram tiles
-    return launch_tc_pass1(A, lda, B, ldb, n, ka, kb, nullptr, 0, out, ldo, nullptr, workspace, workspace_bytes,
+    return launch_tc_pass1(A, lda, B, ldb, n, ka, kb, nullptr, 0, out, ldo, nullptr, workspace, workspace_bytes, false,
                            (cudaStream_t)stream);
   return launch_tn(A, lda, ka, nullptr, 0, 0, B, ldb, kb, n, 0, nullptr, 0, out, ldo, nullptr, workspace,
                    workspace_bytes, (cudaStream_t)stream);

@@ -96,6 +96,14 @@ constexpr int kSmemBytes = kRaw * kRawBytes + kLo * kBBytes + 1024 /*align*/ + 5
 // (lo(x) <= 2^-10 |x|, hence the extra 2^11), so all four sit around 2^-4 with maxima near 1 whatever the units of
 // A and B are.  Both terms come out scaled by 2^g, g = 11 - eA - eB; the hi.hi term is brought to the same scale by
 // writing a 2^g (exact) as its A operand, and the drain warps multiply the finished sums by 2^-g (exact).
+// Two splits live side by side, chosen per launch (template parameter F16):
+//   F16 = true   all three terms on the fp16 pipe (three K = 16 fp16 MMAs per stage, 1.5 TF32-pass equivalents): the
+//                large data passes (V^T [V | Z], Z - V W, Vb, the structured route's products);
+//   F16 = false  hi.hi as 2 x kind::tf32 on the raw fp32 tile, the two correction terms in fp16 with their own scale (2.0
+//                pass equivalents): the Q-space block GEMMs, whose operands (Cholesky factor, its inverse) span many
+//                orders of magnitude -- the common scale of the fp16 split gives elements below 2^-10 of the largest
+//                one absolute instead of relative precision, which cond(B) ~ 1e4 amplifies (c1 at lvs = (2, -4): W
+//                error 1.7e-3 against 2.7e-4, dNLL/dZ 1.1e-4 against 1.5e-5; experiments/bench/c1_diag.py).
 struct F16Scales {
   float a32, a_hi, a_lo, b_hi, b_lo, out;
 };
@@ -106,12 +114,43 @@ __device__ __forceinline__ int exp_of_bits(const uint32_t* p) {
   const int e = (int)((b >> 23) & 0xFF) - 126;   // 2^(e-1) <= max|x| < 2^e
   return e < -50 ? -50 : (e > 50 ? 50 : e);
 }
+// The 11 leading significant bits of an fp32 number (given as its bit pattern): the tf32 pipe truncates, so its split
+// truncates too; the fp16 split rounds (half away from zero), which halves the remainder and makes its sign random --
+// the dropped lo.lo term is then zero-mean instead of a coherent bias.
+template <bool F16>
+__device__ __forceinline__ float hi11(uint32_t bits) {
+  return __uint_as_float(F16 ? ((bits + 0x1000u) & 0xFFFFE000u) : (bits & 0xFFFFE000u));
+}
+// fp16 split: hi = the operand rounded to 11 significant bits (exactly an fp16 number), lo = the remainder rounded to
+// fp16, BOTH scaled by the same power of two per operand, 2^(kF16Top - e) with max|x| < 2^e, so that hi.hi, hi.lo and
+// lo.hi share one scale and one accumulator.  kF16Top = 7 puts the largest magnitude below 128: 2^8 of headroom to the
+// fp16 maximum for rows the magnitude sample did not see, and a remainder that stays a normal fp16 number for every
+// element above 2^-10 of the maximum (below that the error is bounded by 2^-32 of the maximum).
+constexpr int kF16Top = 7;
+// The tensor core adds into its fp32 accumulator with truncation, which on coherent (same-sign) sums is a relative bias
+// of -1.4e-7 ... -3.1e-7 for this window schedule, depending on the spread of the magnitudes (experiments/bench/
+// bias_cal.py; the tf32 split measures -0.4e-7 ... -2.8e-7, part of it hidden by its over-counted lo.lo term).  The
+// fp16 split scales the finished sums by 1 + kRzComp in the drain (one fused multiply-add, rounded to nearest), which
+// centres it: +0.5e-7 ... -1.1e-7 on the same data.
+template <bool F16>
+struct RzComp { static constexpr float value = F16 ? 2.0e-7f : 0.f; };
+// tf32 split: each fp16 factor of the correction terms is normalised by its own operand's magnitude,
+//   a.lo(b) -> (a 2^-eA) . (lo(b) 2^(11 - eB))      lo(a).b -> (lo(a) 2^(11 - eA)) . (b 2^-eB)
+// both scaled by 2^g, g = 11 - eA - eB; hi.hi is brought to the same scale by writing a 2^g (exact) as its A operand.
+template <bool F16>
 __device__ __forceinline__ F16Scales make_scales(int eA, int eB) {
-  const int g = 11 - eA - eB;
   F16Scales s;
-  s.a32 = exp2f((float)g);          s.out = exp2f((float)-g);
-  s.a_hi = exp2f((float)-eA);       s.a_lo = exp2f((float)(11 - eA));
-  s.b_hi = exp2f((float)-eB);       s.b_lo = exp2f((float)(11 - eB));
+  if (F16) {
+    s.a32 = 1.f;
+    s.a_hi = s.a_lo = exp2f((float)(kF16Top - eA));
+    s.b_hi = s.b_lo = exp2f((float)(kF16Top - eB));
+    s.out = exp2f((float)(eA + eB - 2 * kF16Top));
+  } else {
+    const int g = 11 - eA - eB;
+    s.a32 = exp2f((float)g);          s.out = exp2f((float)-g);
+    s.a_hi = exp2f((float)-eA);       s.a_lo = exp2f((float)(11 - eA));
+    s.b_hi = exp2f((float)-eB);       s.b_lo = exp2f((float)(11 - eB));
+  }
   return s;
 }
 
@@ -241,7 +280,7 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
 // Explicit shared-space accesses, all loads before the first store (through generic pointers the compiler kept every
 // load behind the previous store).  A_MN: the raw A tile is MN-major (pass 1: [k-row][32-float group],
 // SWIZZLE_128B_BASE32B) or K-major (row GEMM: [row][16 floats], SWIZZLE_64B).
-template <bool A_MN>
+template <bool A_MN, bool F16>
 __device__ __forceinline__ void convert_a_stage(uint8_t* base, TcShared* sm, uint32_t tmem, uint32_t conv0_leader,
                                                 uint32_t it, const F16Scales& sc, unsigned long long& pw0,
                                                 unsigned long long& pw1) {
@@ -270,23 +309,31 @@ __device__ __forceinline__ void convert_a_stage(uint8_t* base, TcShared* sm, uin
 #pragma unroll
   for (int c = 0; c < TBK / 2; ++c) {
     const float x0 = __uint_as_float(ahi[2 * c]), x1 = __uint_as_float(ahi[2 * c + 1]);
-    const float l0 = x0 - __uint_as_float(ahi[2 * c] & 0xFFFFE000u), l1 = x1 - __uint_as_float(ahi[2 * c + 1] & 0xFFFFE000u);
-    a16[c] = pack_f16x2(x0 * sc.a_hi, x1 * sc.a_hi);               // even k in the low half of the TMEM column
+    const float l0 = x0 - hi11<F16>(ahi[2 * c]), l1 = x1 - hi11<F16>(ahi[2 * c + 1]);
+    // even k in the low half of the TMEM column
+    a16[c] = F16 ? pack_f16x2((x0 - l0) * sc.a_hi, (x1 - l1) * sc.a_hi) : pack_f16x2(x0 * sc.a_hi, x1 * sc.a_hi);
     a16[TBK / 2 + c] = pack_f16x2(l0 * sc.a_lo, l1 * sc.a_lo);
   }
+  if (!F16) {
 #pragma unroll
-  for (int k = 0; k < TBK; ++k) ahi[k] = __float_as_uint(__uint_as_float(ahi[k]) * sc.a32);   // exact
+    for (int k = 0; k < TBK; ++k) ahi[k] = __float_as_uint(__uint_as_float(ahi[k]) * sc.a32);   // exact
+  }
   PROF_WAIT(pw1, mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1));
   tcgen05_fence_after();
   const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + kAccCols + sl * kASlotCols;
-  tmem_st_32x16(ta, ahi);
-  tmem_st_32x16(ta + TBK, a16);
+  if (F16) {
+    tmem_st_32x16(ta, a16);            // columns [0, 8): hi, [8, 16): lo
+  } else {
+    tmem_st_32x16(ta, ahi);            // columns [0, 16): a 2^g (fp32), [16, 24): a (fp16), [24, 32): lo(a)
+    tmem_st_32x16(ta + TBK, a16);
+  }
   tmem_wait_st();
   tcgen05_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(conv0_leader + 8u * sl);
 }
 
+template <bool F16>
 __device__ __forceinline__ void convert_b_stage(uint8_t* base, TcShared* sm, uint32_t conv0_leader, uint32_t it,
                                                 const F16Scales& sc) {
   const int lane = threadIdx.x & 31, w2 = (threadIdx.x >> 5) - 2;
@@ -312,11 +359,12 @@ __device__ __forceinline__ void convert_b_stage(uint8_t* base, TcShared* sm, uin
     const int chunk = 4 * bb + ((qb >> 1) ^ (kb & 3));          // logical 8-column chunk within the 64-column group
     const uint32_t dst = bplane + jj * 2048 + (kb >> 3) * 1024 + (kb & 7) * 128 + ((chunk ^ (kb & 7)) << 4) + (qb & 1) * 8;
     const float4 v = bv[i];
-    const uint32_t h0 = pack_f16x2(v.x * sc.b_hi, v.y * sc.b_hi), h1 = pack_f16x2(v.z * sc.b_hi, v.w * sc.b_hi);
-    const float lx = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    const float ly = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    const float lz = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    const float lw = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    const float lx = v.x - hi11<F16>(__float_as_uint(v.x));
+    const float ly = v.y - hi11<F16>(__float_as_uint(v.y));
+    const float lz = v.z - hi11<F16>(__float_as_uint(v.z));
+    const float lw = v.w - hi11<F16>(__float_as_uint(v.w));
+    const uint32_t h0 = F16 ? pack_f16x2((v.x - lx) * sc.b_hi, (v.y - ly) * sc.b_hi) : pack_f16x2(v.x * sc.b_hi, v.y * sc.b_hi);
+    const uint32_t h1 = F16 ? pack_f16x2((v.z - lz) * sc.b_hi, (v.w - lw) * sc.b_hi) : pack_f16x2(v.z * sc.b_hi, v.w * sc.b_hi);
     const uint32_t l0 = pack_f16x2(lx * sc.b_lo, ly * sc.b_lo), l1 = pack_f16x2(lz * sc.b_lo, lw * sc.b_lo);
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kBBytes / 2), "r"(l0), "r"(l1) : "memory");
@@ -334,6 +382,7 @@ __device__ __forceinline__ bool win_ends(int g, int ngroups) { return g == ngrou
 
 // MMA issuer (one thread of the leader): group g of a unit (stages [it, it + gst)).
 // wc: windows issued so far (barrier phase).
+template <bool F16>
 __device__ __forceinline__ void issue_group(uint8_t* base, TcShared* sm, uint32_t tmem, uint32_t it, int gst, int g,
                                             int ngroups, uint32_t& wc, unsigned long long& pw0,
                                             unsigned long long& pw1) {
@@ -352,18 +401,25 @@ __device__ __forceinline__ void issue_group(uint8_t* base, TcShared* sm, uint32_
     // one K = 16 fp16 MMA per correction term: (a 2^-6) . (b_lo 2^6) and (a_lo 2^6) . (b 2^-6)
     constexpr uint32_t idesc16 = umma_idesc_f16(TM, TN, false, true);
     const uint32_t b16 = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
-    const uint32_t a16 = tmem + kAccCols + sl * kASlotCols + TBK;
+    const uint32_t a16 = tmem + kAccCols + sl * kASlotCols + (F16 ? 0 : TBK);
     umma_f16_pair_ts(d, a16, umma_desc(b16 + kBBytes / 2, GPP_TC_F16_LBO, GPP_TC_F16_SBO, kLayoutSw128), idesc16, acc);
     umma_f16_pair_ts(d, a16 + TBK / 2, umma_desc(b16, GPP_TC_F16_LBO, GPP_TC_F16_SBO, kLayoutSw128), idesc16, 1);
     acc = 1;
   }
   for (int j = 0; j < gst; ++j) {   // then the hi.hi terms
     const int s = (it + j) % kRaw, sl = (it + j) % kLo;
-    const uint32_t b_hi = smem_u32(base + s * kRawBytes) + kABytes;
-    const uint32_t a_hi = tmem + kAccCols + sl * kASlotCols;
+    if (F16) {
+      constexpr uint32_t idesc16 = umma_idesc_f16(TM, TN, false, true);
+      const uint32_t b16 = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
+      umma_f16_pair_ts(d, tmem + kAccCols + sl * kASlotCols, umma_desc(b16, GPP_TC_F16_LBO, GPP_TC_F16_SBO, kLayoutSw128),
+                       idesc16, 1);
+    } else {
+      const uint32_t b_hi = smem_u32(base + s * kRawBytes) + kABytes;
+      const uint32_t a_hi = tmem + kAccCols + sl * kASlotCols;
 #pragma unroll
-    for (int kk = 0; kk < TBK / 8; ++kk)
-      umma_tf32_pair_ts(d, a_hi + kk * 8, umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32), idesc, 1);
+      for (int kk = 0; kk < TBK / 8; ++kk)
+        umma_tf32_pair_ts(d, a_hi + kk * 8, umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32), idesc, 1);
+    }
     umma_commit_pair(&sm->empty[s], 3);       // raw tile, B lo plane and A slot are free in both CTAs
     umma_commit_pair(&sm->lo_empty[sl], 3);
   }
@@ -397,6 +453,7 @@ __device__ __forceinline__ void drain_group(TcShared* sm, uint32_t tmem, uint32_
 }
 
 // =====================================================================================================
+template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmX, Pass1Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -414,7 +471,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       // ===================================================== B converters
       const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
       const int eV = exp_of_bits(p.amax), eX = exp_of_bits(p.amax ? p.amax + 1 : nullptr);
-      const F16Scales sc_g = make_scales(eV, eV), sc_c = make_scales(eV, eX);
+      const F16Scales sc_g = make_scales<F16>(eV, eV), sc_c = make_scales<F16>(eV, eX);
       uint32_t it = 0;
       for (int u = pair; u < nunits; u += npairs) {
         const int split = u / p.tiles, tile = u - split * p.tiles;
@@ -422,7 +479,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
         const int64_t r1 = min(p.n, r0 + p.rows_per_split);
         const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
         const F16Scales sc = tile < p.tiles_g ? sc_g : sc_c;
-        for (int st = 0; st < nst; ++st, ++it) convert_b_stage(base, sm, conv0, it, sc);
+        for (int st = 0; st < nst; ++st, ++it) convert_b_stage<F16>(base, sm, conv0, it, sc);
       }
     } else if (warp == 0 && lane == 0) {
       // ===================================================== TMA producer (this CTA's halves of A and B)
@@ -485,7 +542,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
         const int ngroups = (nst + kGroup - 1) / kGroup;
         for (int g = 0; g < ngroups; ++g) {
           const int gst = min(kGroup, nst - g * kGroup);
-          issue_group(base, sm, tmem, it, gst, g, ngroups, wc, pw0, pw1);
+          issue_group<F16>(base, sm, tmem, it, gst, g, ngroups, wc, pw0, pw1);
           it += gst;
         }
       }
@@ -497,7 +554,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
     PROF_DECL;
     const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
     const int eV = exp_of_bits(p.amax), eX = exp_of_bits(p.amax ? p.amax + 1 : nullptr);
-    const F16Scales sc_g = make_scales(eV, eV), sc_c = make_scales(eV, eX);
+    const F16Scales sc_g = make_scales<F16>(eV, eV), sc_c = make_scales<F16>(eV, eX);
     uint32_t it = 0;
     for (int u = pair; u < nunits; u += npairs) {
       const int split = u / p.tiles, tile = u - split * p.tiles;
@@ -505,7 +562,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       const int64_t r1 = min(p.n, r0 + p.rows_per_split);
       const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
       const F16Scales sc = tile < p.tiles_g ? sc_g : sc_c;
-      for (int st = 0; st < nst; ++st, ++it) convert_a_stage<true>(base, sm, tmem, conv0, it, sc, pw0, pw1);
+      for (int st = 0; st < nst; ++st, ++it) convert_a_stage<true, F16>(base, sm, tmem, conv0, it, sc, pw0, pw1);
     }
     if (threadIdx.x == 128) PROF_STORE(2);
   } else {
@@ -515,7 +572,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
     const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
     const int q = warp & 3, cb = (warp - 8) >> 2;
     const int eV = exp_of_bits(p.amax), eX = exp_of_bits(p.amax ? p.amax + 1 : nullptr);
-    const float out_g = make_scales(eV, eV).out, out_c = make_scales(eV, eX).out;
+    const float out_g = make_scales<F16>(eV, eV).out, out_c = make_scales<F16>(eV, eX).out;
     uint32_t wc = 0;
     for (int u = pair; u < nunits; u += npairs) {
       const int split = u / p.tiles, tile = u - split * p.tiles;
@@ -531,8 +588,12 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       float* out = p.partial + ((size_t)tile * p.splits + split) * (size_t)(TM * TN) +
                    (size_t)(rank * HM + q * 32 + lane) * TN + cb * 128;
 #pragma unroll
-      for (int i = 0; i < 128; i += 4)
-        *reinterpret_cast<float4*>(out + i) = make_float4(os * acc[i], os * acc[i + 1], os * acc[i + 2], os * acc[i + 3]);
+      for (int i = 0; i < 128; i += 4) {
+        constexpr float kc = RzComp<F16>::value;
+        const float y0 = os * acc[i], y1 = os * acc[i + 1], y2 = os * acc[i + 2], y3 = os * acc[i + 3];
+        *reinterpret_cast<float4*>(out + i) =
+            make_float4(fmaf(y0, kc, y0), fmaf(y1, kc, y1), fmaf(y2, kc, y2), fmaf(y3, kc, y3));
+      }
     }
     if (threadIdx.x == 256) PROF_STORE(3);
   }
@@ -636,12 +697,14 @@ __device__ __forceinline__ RowsUnit rows_unit(const RowsParams& p, int64_t u, in
 }
 
 // one scale set per launch: the [A1 | A2] parts share the accumulator, hence the common scale (larger magnitude wins)
+template <bool F16>
 __device__ __forceinline__ F16Scales rows_scales(const RowsParams& p) {
   int eA = exp_of_bits(p.amax);
   if (p.K2 > 0 && p.amax) eA = max(eA, exp_of_bits(p.amax + 2));
-  return make_scales(eA, exp_of_bits(p.amax ? p.amax + 1 : nullptr));
+  return make_scales<F16>(eA, exp_of_bits(p.amax ? p.amax + 1 : nullptr));
 }
 
+template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, RowsParams p) {
@@ -660,11 +723,11 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     setmaxnreg_dec<80>();
     if (warp >= 2) {
       const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
-      const F16Scales sc = rows_scales(p);
+      const F16Scales sc = rows_scales<F16>(p);
       uint32_t it = 0;
       for (int64_t u = pair; u < nunits; u += npairs) {
         const RowsUnit un = rows_unit(p, u, nst);
-        for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_b_stage(base, sm, conv0, it, sc);
+        for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_b_stage<F16>(base, sm, conv0, it, sc);
       }
     } else if (warp == 0 && lane == 0) {
       PROF_DECL;
@@ -705,7 +768,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int ngroups = (ust + kGroup - 1) / kGroup;
         for (int g = 0; g < ngroups; ++g) {
           const int gst = min(kGroup, ust - g * kGroup);
-          issue_group(base, sm, tmem, it, gst, g, ngroups, wc, pw0, pw1);
+          issue_group<F16>(base, sm, tmem, it, gst, g, ngroups, wc, pw0, pw1);
           it += gst;
         }
       }
@@ -716,10 +779,10 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     PROF_DECL;
     const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
     uint32_t it = 0;
-    const F16Scales sc = rows_scales(p);
+    const F16Scales sc = rows_scales<F16>(p);
     for (int64_t u = pair; u < nunits; u += npairs) {
       const RowsUnit un = rows_unit(p, u, nst);
-      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_a_stage<false>(base, sm, tmem, conv0, it, sc, pw0, pw1);
+      for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_a_stage<false, F16>(base, sm, tmem, conv0, it, sc, pw0, pw1);
     }
     if (threadIdx.x == 128) PROF_STORE(2);
   } else {
@@ -730,7 +793,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     uint32_t wc = 0;
     float alpha = p.alpha_host;
     if (p.mode == 0 && p.scal) alpha = (float)(1.0 / p.scal[GPP_S_VN]);
-    const float os = rows_scales(p).out;
+    const float os = rows_scales<F16>(p).out;
     for (int64_t u = pair; u < nunits; u += npairs) {
       const RowsUnit un = rows_unit(p, u, nst);
       const int64_t rt = un.rt;
@@ -742,7 +805,10 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
       for (int g = 0; g < ngroups; ++g) drain_group(sm, tmem, tempty0, g, ngroups, wc, acc, pw0);
 #pragma unroll
-      for (int i = 0; i < 128; ++i) acc[i] *= os;   // undo the common power-of-two scale of the split (exact)
+      for (int i = 0; i < 128; ++i) {   // undo the common power-of-two scale of the split (exact), centre the RZ bias
+        const float y = acc[i] * os;
+        acc[i] = fmaf(y, RzComp<F16>::value, y);
+      }
       // ---- epilogue for this unit: this CTA's 128 rows, this warp's 128 columns
       const int64_t row = rt * TM + rank * HM + q * 32 + lane;
       const int col0 = ct * TN + cb * 128;
@@ -877,16 +943,18 @@ int pair_count(K kernel) {
 int pass1_pairs() {
   static int n = 0;
   if (n == 0) {
-    cudaFuncSetAttribute(tc_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    n = pair_count(tc_pass1_kernel);
+    cudaFuncSetAttribute(tc_pass1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(tc_pass1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    n = pair_count(tc_pass1_kernel<true>);
   }
   return n;
 }
 int rows_pairs() {
   static int n = 0;
   if (n == 0) {
-    cudaFuncSetAttribute(tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    n = pair_count(tc_rows_kernel);
+    cudaFuncSetAttribute(tc_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaFuncSetAttribute(tc_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    n = pair_count(tc_rows_kernel<true>);
   }
   return n;
 }
@@ -946,7 +1014,7 @@ size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g) {
 // G (Q x Q, optional) = V^T V and C (Q x L) = V^T X [* v0/vn when scal_c is set]; G == nullptr skips the Gram tiles.
 int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* G,
                     int64_t ldg, float* C, int64_t ldc, const double* scal_c, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
+                    bool wide_range, cudaStream_t st) {
   Pass1Params p;
   pass1_geometry(n, Q, L, G == nullptr, p);
   const size_t part_bytes = (size_t)p.tiles * p.splits * TM * TN * sizeof(float), need = part_bytes + 256;
@@ -972,7 +1040,8 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
   else tmX = tmV;
   const int nunits = p.tiles * p.splits;
   const int pairs = nunits < pass1_pairs() ? nunits : pass1_pairs();
-  tc_pass1_kernel<<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmV, tmX, p);
+  if (wide_range) tc_pass1_kernel<false><<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmV, tmX, p);
+  else tc_pass1_kernel<true><<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmV, tmX, p);
   GPP_LAUNCH_CHECK();
   tc_reduce_kernel<<<p.tiles * 8, 256, 0, st>>>(p);
   GPP_LAUNCH_CHECK();
@@ -994,7 +1063,7 @@ size_t tc_xb_workspace_bytes(int64_t n, int L) {
 }
 
 static int launch_rows_maps(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB, int64_t n,
-                            int K1, int K2, int ncols, RowsParams& p, cudaStream_t st) {
+                            int K1, int K2, int ncols, RowsParams& p, bool wide_range, cudaStream_t st) {
   p.n = n; p.K1 = K1; p.K2 = K2; p.ncols = ncols;
   if (p.batches <= 0) p.batches = 1;
   if (p.n_last <= 0) p.n_last = n;
@@ -1003,7 +1072,8 @@ static int launch_rows_maps(const CUtensorMap& tmA1, const CUtensorMap& tmA2, co
   const int64_t nunits = (p.lower_only ? p.row_tiles * (p.row_tiles + 1) / 2 : p.row_tiles * p.col_tiles) * p.batches;
   const int pairs = (int)(nunits < rows_pairs() ? nunits : rows_pairs());
   if (pairs <= 0) return GPP_OK;
-  tc_rows_kernel<<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmA1, tmA2, tmB, p);
+  if (wide_range) tc_rows_kernel<false><<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmA1, tmA2, tmB, p);
+  else tc_rows_kernel<true><<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmA1, tmA2, tmB, p);
   GPP_LAUNCH_CHECK();
   return GPP_OK;
 }
@@ -1021,7 +1091,7 @@ static int launch_rows(const float* A1, int64_t lda1, int K1, const float* A2, i
   if (K2 > 0) GPP_TRY(make_map_2d(&tmA2, A2, n, K2, lda2, TBK, HM, CU_TENSOR_MAP_SWIZZLE_64B));
   else tmA2 = tmA1;
   GPP_TRY(make_map_2d(&tmB, B, (int64_t)K1 + K2, ncols, ldb, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  return launch_rows_maps(tmA1, tmA2, tmB, n, K1, K2, ncols, p, st);
+  return launch_rows_maps(tmA1, tmA2, tmB, n, K1, K2, ncols, p, false, st);
 }
 
 // Batched block GEMM inside larger row-major matrices (the Q-space solves):
@@ -1043,7 +1113,7 @@ int launch_tc_blockgemm(const float* Amat, int64_t a_rows, int64_t a_cols, int64
   p.a_row0 = g.a_row0; p.a_row_step = g.a_row_step; p.a_k0 = g.a_k0; p.a_k_step = g.a_k_step;
   p.b_k0 = g.b_k0; p.b_k_step = g.b_k_step; p.b_col0 = g.b_col0; p.b_col_step = g.b_col_step;
   p.tri_a = g.tri_a; p.tri_b = g.tri_b; p.out_step = g.out_step; p.amax = amax;
-  return launch_rows_maps(tmA, tmA, tmB, g.n, g.K, 0, g.ncols, p, st);
+  return launch_rows_maps(tmA, tmA, tmB, g.n, g.K, 0, g.ncols, p, g.wide_range != 0, st);
 }
 
 // Symmetric rank-K update of the lower block triangle, in place:  C -= A A^T  with A (n x K, ld = lda) and its transpose
@@ -1055,7 +1125,7 @@ int launch_tc_syrk_sub(float* C, int64_t ldc, const float* A, int64_t lda, const
   GPP_TRY(make_map_2d(&tmB, At, K, n, ldat, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   RowsParams p{};
   p.mode = 0; p.X = C; p.ldx = ldc; p.out = C; p.ldo = ldc; p.alpha_host = 1.f; p.lower_only = 1; p.amax = amax;
-  return launch_rows_maps(tmA, tmA, tmB, n, K, 0, n, p, st);
+  return launch_rows_maps(tmA, tmA, tmB, n, K, 0, n, p, true, st);
 }
 
 // out = alpha (X - A M); with nll != nullptr also the NLL epilogue (quad partials -> xb_finalize).

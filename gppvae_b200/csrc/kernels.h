@@ -39,7 +39,7 @@ bool tc_pass1_supported(int64_t n, int Q, int L);
 size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g);
 int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* G,
                     int64_t ldg, float* C, int64_t ldc, const double* scal_c, void* ws, size_t ws_bytes,
-                    cudaStream_t st);
+                    bool wide_range, cudaStream_t st);
 
 // batched block GEMM on the tensor cores (see gemm_tc.cu)
 struct TcBlockGemm {
@@ -47,6 +47,7 @@ struct TcBlockGemm {
   int a_row0, a_row_step, a_k0, a_k_step, b_k0, b_k_step, b_col0, b_col_step, tri_a, tri_b;
   int64_t out_step;
   float alpha;
+  int wide_range;   // operands span many orders of magnitude (Cholesky factor, its inverse): tf32 hi.hi split, see gemm_tc.cu
 };
 bool tc_blockgemm_supported(int n, int K, int ncols);
 // amax (device, may be null): [0] bit pattern of max|A|, [1] of max|B| -- the magnitudes the fp16 scales of the

@@ -718,12 +718,14 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
     if (tc_blockgemm_supported(b, b, b)) {
       // large levels on the tensor cores (3xTF32): T = C . Ai, then X = -Di . T
       TcBlockGemm g{};
+      g.wide_range = 1;
       g.n = b; g.n_last = m_last; g.K = b; g.ncols = b; g.batches = npairs; g.out_step = pair_stride;
       g.a_row0 = b; g.a_row_step = 2 * b; g.a_k0 = 0; g.a_k_step = 2 * b;       // C block of Lc: rows p0 + b, cols p0
       g.b_k0 = 0; g.b_k_step = 2 * b; g.b_col0 = 0; g.b_col_step = 2 * b;       // Ai: rows p0, cols p0
       g.tri_b = 1; g.alpha = 1.f;
       GPP_TRY(launch_tc_blockgemm(Bm, Qp, Qp, Qp, Linv, Qp, Qp, Qp, Tm + (int64_t)b * Qp, Qp, g, amax, st));
       TcBlockGemm x{};
+      x.wide_range = 1;
       x.n = b; x.n_last = m_last; x.K = b; x.ncols = b; x.batches = npairs; x.out_step = pair_stride;
       x.a_row0 = b; x.a_row_step = 2 * b; x.a_k0 = b; x.a_k_step = 2 * b;       // Di: rows p0 + b, cols p0 + b
       x.b_k0 = b; x.b_k_step = 2 * b; x.b_col0 = 0; x.b_col_step = 2 * b;       // T: rows p0 + b, cols p0
@@ -751,7 +753,7 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
       return GPP_ERR_INVALID_ARGUMENT;
     }
     if (tc_pass1_supported(Q, Q, 0))
-      GPP_TRY(launch_tc_pass1(Linv, Qp, nullptr, 0, Q, Q, 0, Binv, Q, nullptr, 0, nullptr, tnws, f.tn_bytes, st));
+      GPP_TRY(launch_tc_pass1(Linv, Qp, nullptr, 0, Q, Q, 0, Binv, Q, nullptr, 0, nullptr, tnws, f.tn_bytes, true, st));
     else
       GPP_TRY(launch_tn(Linv, Qp, Q, Linv, Qp, Q, nullptr, 0, 0, Q, 1, Binv, Q, nullptr, 0, nullptr, tnws, f.tn_bytes, st));
   }
@@ -785,13 +787,14 @@ int launch_solve_w(const float* C, int64_t ldc, int Q, int L, int L_true, int64_
   if (tc_blockgemm_supported(Q, Q, L) && tc_pass1_supported(Q, Q, L)) {
     // tensor cores (3xTF32): T1 = Linv . C as a row GEMM, W = (v0/vn) Linv^T T1 as a transposed-A GEMM
     TcBlockGemm g{};
+    g.wide_range = 1;
     g.n = Q; g.n_last = Q; g.K = Q; g.ncols = L; g.batches = 1; g.tri_a = 1; g.alpha = 1.f;
     uint32_t* amax = reinterpret_cast<uint32_t*>(base + sl.off_amax);   // {1 (Linv), max|C|}
     GPP_TRY(tc_absmax(C, ldc, Q, L, amax + 1, st));
     amax_slots_kernel<<<1, 32, 0, st>>>(amax, 1);
     GPP_LAUNCH_CHECK();
     GPP_TRY(launch_tc_blockgemm(Linv, Q, Q, Qp, C, Q, L, ldc, T1, L, g, amax, st));
-    GPP_TRY(launch_tc_pass1(Linv, Qp, T1, L, Q, Q, L, nullptr, 0, W, ldw, scal, tnws, sl.tn_bytes, st));
+    GPP_TRY(launch_tc_pass1(Linv, Qp, T1, L, Q, Q, L, nullptr, 0, W, ldw, scal, tnws, sl.tn_bytes, true, st));
   } else {
     GemmParams g{};
     g.A = Linv; g.lda = Qp; g.B = C; g.ldb = ldc; g.C = T1; g.ldc = L;
