@@ -16,7 +16,7 @@ torch.cuda.synchronize()
 lib = ctypes.CDLL(L.LIB_PATH)
 buf = np.zeros((512, 16), dtype=np.uint64)
 assert lib.gpp_debug_prof(buf.ctypes.data_as(ctypes.c_void_p)) == 0
-names = ["producer (wait empty)", "mma (wait tempty | wait conv)", "converter (wait full | wait lo_empty)", "drain (wait tfull)"]
+names = ["producer (wait empty)", "mma (wait tempty | wait conv)", "A converter (wait full | wait lo_empty)", "drain (wait tfull)", "B converter (wait full | wait lo_empty)"]
 for rank in (0, 1):
     rows = buf[rank::2][:74].astype(np.float64)
     for r, nm in enumerate(names):

@@ -45,7 +45,7 @@ using namespace gpp;
 
 extern "C" int gpp_version(void) { return 100; }
 extern "C" const char* gpp_last_error(void) { return g_last_error.c_str(); }
-extern "C" const char* gpp_gemm_engine(void) { return "tcgen05-tf32+2xf16"; }
+extern "C" const char* gpp_gemm_engine(void) { return "tcgen05-3xf16"; }
 extern "C" uint64_t gpp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------ pass 1
@@ -62,7 +62,7 @@ extern "C" int gpp_gram_vtz(const float* V, int64_t ldv, const float* X, int64_t
   GPP_REQUIRE(mat_ok(V, ldv, Q), "gram_vtz: V must be 16-byte aligned with ldv >= Q and ldv %% 4 == 0");
   GPP_REQUIRE(L == 0 || mat_ok(X, ldx, L), "gram_vtz: X must be 16-byte aligned with ldx >= L and ldx %% 4 == 0");
   GPP_REQUIRE(mat_ok(GC, ldgc, (int64_t)Q + L), "gram_vtz: GC must be 16-byte aligned with ldgc >= Q + L");
-  // large problems run on the tensor cores (3xTF32); tiles that cannot fill a 256 x 256 pair UMMA use the fp32 tile engine
+  // large problems run on the tensor cores (3-term split); tiles that cannot fill a 256 x 256 pair UMMA use the fp32 tile engine
   if (tc_pass1_supported(n, Q, L))
     return launch_tc_pass1(V, ldv, X, ldx, n, Q, L, GC, ldgc, GC + Q, ldgc, nullptr, workspace, workspace_bytes, false,
                            (cudaStream_t)stream);

@@ -231,12 +231,16 @@ template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- pieces shared by the two kernels ----------------------------------------------------------------------
+// F16: the raw tiles are read by the converter warps only (the MMAs take all operands from the fp16 planes / TMEM), so a
+// raw slot is handed back to the TMA producer by its six local converter warps as soon as they hold it in registers --
+// not by the MMA commit, which in the tf32 split keeps a slot for the whole correction-terms-first group.
+template <bool F16>
 __device__ __forceinline__ TcShared* tc_prologue(uint8_t* base, uint32_t& tmem) {
   TcShared* sm = reinterpret_cast<TcShared*>(base + kRaw * kRawBytes + kLo * kBBytes);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRaw; ++s) {
       mbar_init(&sm->full[s], 1);
-      mbar_init(&sm->empty[s], 1);
+      mbar_init(&sm->empty[s], F16 ? 6 : 1);
     }
     for (int s = 0; s < kLo; ++s) {
       mbar_init(&sm->conv[s], 12);    // (4 A + 2 B converter warps) x 2 CTAs (used in the leader)
@@ -271,6 +275,37 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+
+// The B half-tile of a stage (16 k-rows x 128 columns of fp32) is converted in 16 units of one float4 per lane: unit m
+// covers 64-column group m & 1 and k-rows 2 (m >> 1) + {0, 1}.  float4 (k-row kb, 32-float group 2 jj + bb, 16-byte
+// position qb) is chosen so that 16 lanes cover the 64 columns of one fp16 row: conflict-free 128-bit loads and
+// conflict-free 64-bit stores into the fp16 planes (hi plane at +0, lo plane at +4 KB), each MN-major SWIZZLE_128B:
+// 64-column group g at g * 2 KB, k-row k at (k / 8) * 1 KB + (k % 8) * 128 B, 16-byte chunk ((c % 64) / 8) ^ (k % 8),
+// element (c % 8) * 2 B.
+// Eight units per B-converter warp.  (Giving the four A-converter warps one unit each was measured: no gain -- the
+// kernel is bound by the L2 -> shared-memory stream of the raw tiles, not by the converters.)
+constexpr int kBUnitsB = 8;
+
+__device__ __forceinline__ float4 b_unit_load(uint32_t braw, int m, int lane) {
+  const int qb = lane & 7, bb = (lane >> 3) & 1, kpar = lane >> 4;
+  const int jj = m & 1, kb = 2 * (m >> 1) + kpar;
+  return lds_f32x4(braw + (2 * jj + bb) * (TBK * 128) + kb * 128 + qb * 16);
+}
+template <bool F16>
+__device__ __forceinline__ void b_unit_store(uint32_t bplane, int m, int lane, const float4 v, const F16Scales& sc) {
+  const int qb = lane & 7, bb = (lane >> 3) & 1, kpar = lane >> 4;
+  const int jj = m & 1, kb = 2 * (m >> 1) + kpar;
+  const int chunk = 4 * bb + ((qb >> 1) ^ (kb & 3));          // logical 8-column chunk within the 64-column group
+  const uint32_t dst = bplane + jj * 2048 + (kb >> 3) * 1024 + (kb & 7) * 128 + ((chunk ^ (kb & 7)) << 4) + (qb & 1) * 8;
+  const float hx = hi11<F16>(__float_as_uint(v.x)), hy = hi11<F16>(__float_as_uint(v.y));
+  const float hz = hi11<F16>(__float_as_uint(v.z)), hw = hi11<F16>(__float_as_uint(v.w));
+  const uint32_t h0 = F16 ? pack_f16x2(hx * sc.b_hi, hy * sc.b_hi) : pack_f16x2(v.x * sc.b_hi, v.y * sc.b_hi);
+  const uint32_t h1 = F16 ? pack_f16x2(hz * sc.b_hi, hw * sc.b_hi) : pack_f16x2(v.z * sc.b_hi, v.w * sc.b_hi);
+  const uint32_t l0 = pack_f16x2((v.x - hx) * sc.b_lo, (v.y - hy) * sc.b_lo);
+  const uint32_t l1 = pack_f16x2((v.z - hz) * sc.b_lo, (v.w - hw) * sc.b_lo);
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kBBytes / 2), "r"(l0), "r"(l1) : "memory");
 }
 
 // Converter warps.  Two independent chains per stage, so that neither is as long as a tensor-pipe stage:
@@ -314,7 +349,10 @@ __device__ __forceinline__ void convert_a_stage(uint8_t* base, TcShared* sm, uin
     a16[c] = F16 ? pack_f16x2((x0 - l0) * sc.a_hi, (x1 - l1) * sc.a_hi) : pack_f16x2(x0 * sc.a_hi, x1 * sc.a_hi);
     a16[TBK / 2 + c] = pack_f16x2(l0 * sc.a_lo, l1 * sc.a_lo);
   }
-  if (!F16) {
+  if (F16) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm->empty[s]);   // raw tile consumed (values are in registers)
+  } else {
 #pragma unroll
     for (int k = 0; k < TBK; ++k) ahi[k] = __float_as_uint(__uint_as_float(ahi[k]) * sc.a32);   // exact
   }
@@ -335,40 +373,22 @@ __device__ __forceinline__ void convert_a_stage(uint8_t* base, TcShared* sm, uin
 
 template <bool F16>
 __device__ __forceinline__ void convert_b_stage(uint8_t* base, TcShared* sm, uint32_t conv0_leader, uint32_t it,
-                                                const F16Scales& sc) {
+                                                const F16Scales& sc, unsigned long long& pw0, unsigned long long& pw1) {
   const int lane = threadIdx.x & 31, w2 = (threadIdx.x >> 5) - 2;
   const int s = it % kRaw, sl = it % kLo;
-  mbar_wait(&sm->full[s], (it / kRaw) & 1);
-  // float4 (k-row kb, 32-float group 2 jj + bb, 16-byte position qb) chosen so that 16 lanes cover the 64 columns of
-  // one fp16 row: conflict-free 128-bit loads here and conflict-free 64-bit stores into the fp16 planes below
+  PROF_WAIT(pw0, mbar_wait(&sm->full[s], (it / kRaw) & 1));
   const uint32_t braw = smem_u32(base + s * kRawBytes) + kABytes;
-  const int qb = lane & 7, bb = (lane >> 3) & 1, kpar = lane >> 4;
-  float4 bv[8];
+  float4 bv[kBUnitsB];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = w2 * 8 + i, jj = m & 1, kb = 2 * (m >> 1) + kpar;
-    bv[i] = lds_f32x4(braw + (2 * jj + bb) * (TBK * 128) + kb * 128 + qb * 16);
+  for (int i = 0; i < kBUnitsB; ++i) bv[i] = b_unit_load(braw, w2 * kBUnitsB + i, lane);
+  if (F16) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm->empty[s]);   // raw tile consumed (values are in registers)
   }
-  mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1);
-  // fp16 planes (hi plane at +0, lo plane at +4 KB), each MN-major SWIZZLE_128B: 64-column group g at g * 2 KB,
-  // k-row k at (k / 8) * 1 KB + (k % 8) * 128 B, 16-byte chunk ((c % 64) / 8) ^ (k % 8), element (c % 8) * 2 B
+  PROF_WAIT(pw1, mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1));
   const uint32_t bplane = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = w2 * 8 + i, jj = m & 1, kb = 2 * (m >> 1) + kpar;
-    const int chunk = 4 * bb + ((qb >> 1) ^ (kb & 3));          // logical 8-column chunk within the 64-column group
-    const uint32_t dst = bplane + jj * 2048 + (kb >> 3) * 1024 + (kb & 7) * 128 + ((chunk ^ (kb & 7)) << 4) + (qb & 1) * 8;
-    const float4 v = bv[i];
-    const float lx = v.x - hi11<F16>(__float_as_uint(v.x));
-    const float ly = v.y - hi11<F16>(__float_as_uint(v.y));
-    const float lz = v.z - hi11<F16>(__float_as_uint(v.z));
-    const float lw = v.w - hi11<F16>(__float_as_uint(v.w));
-    const uint32_t h0 = F16 ? pack_f16x2((v.x - lx) * sc.b_hi, (v.y - ly) * sc.b_hi) : pack_f16x2(v.x * sc.b_hi, v.y * sc.b_hi);
-    const uint32_t h1 = F16 ? pack_f16x2((v.z - lz) * sc.b_hi, (v.w - lw) * sc.b_hi) : pack_f16x2(v.z * sc.b_hi, v.w * sc.b_hi);
-    const uint32_t l0 = pack_f16x2(lx * sc.b_lo, ly * sc.b_lo), l1 = pack_f16x2(lz * sc.b_lo, lw * sc.b_lo);
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(h0), "r"(h1) : "memory");
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + kBBytes / 2), "r"(l0), "r"(l1) : "memory");
-  }
+  for (int i = 0; i < kBUnitsB; ++i) b_unit_store<F16>(bplane, w2 * kBUnitsB + i, lane, bv[i], sc);
   fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(conv0_leader + 8u * sl);
@@ -420,7 +440,7 @@ __device__ __forceinline__ void issue_group(uint8_t* base, TcShared* sm, uint32_
       for (int kk = 0; kk < TBK / 8; ++kk)
         umma_tf32_pair_ts(d, a_hi + kk * 8, umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32), idesc, 1);
     }
-    umma_commit_pair(&sm->empty[s], 3);       // raw tile, B lo plane and A slot are free in both CTAs
+    if (!F16) umma_commit_pair(&sm->empty[s], 3);   // raw tile (tf32 split), fp16 planes and A slot are free in both CTAs
     umma_commit_pair(&sm->lo_empty[sl], 3);
   }
   if (win_ends(g, ngroups)) {
@@ -462,7 +482,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   uint32_t tmem;
-  TcShared* sm = tc_prologue(base, tmem);
+  TcShared* sm = tc_prologue<F16>(base, tmem);
   const int nunits = p.tiles * p.splits;
 
   if (warp < 4) {
@@ -472,6 +492,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
       const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
       const int eV = exp_of_bits(p.amax), eX = exp_of_bits(p.amax ? p.amax + 1 : nullptr);
       const F16Scales sc_g = make_scales<F16>(eV, eV), sc_c = make_scales<F16>(eV, eX);
+      PROF_DECL;
       uint32_t it = 0;
       for (int u = pair; u < nunits; u += npairs) {
         const int split = u / p.tiles, tile = u - split * p.tiles;
@@ -479,8 +500,9 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
         const int64_t r1 = min(p.n, r0 + p.rows_per_split);
         const int nst = (int)((r1 - r0 + TBK - 1) / TBK);
         const F16Scales sc = tile < p.tiles_g ? sc_g : sc_c;
-        for (int st = 0; st < nst; ++st, ++it) convert_b_stage<F16>(base, sm, conv0, it, sc);
+        for (int st = 0; st < nst; ++st, ++it) convert_b_stage<F16>(base, sm, conv0, it, sc, pw0, pw1);
       }
+      if (threadIdx.x == 64) PROF_STORE(4);
     } else if (warp == 0 && lane == 0) {
       // ===================================================== TMA producer (this CTA's halves of A and B)
       PROF_DECL;
@@ -714,7 +736,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   uint32_t tmem;
-  TcShared* sm = tc_prologue(base, tmem);
+  TcShared* sm = tc_prologue<F16>(base, tmem);
   const int64_t nunits = (p.lower_only ? p.row_tiles * (p.row_tiles + 1) / 2 : p.row_tiles * p.col_tiles) * p.batches;
   const int nst1 = (p.K1 + TBK - 1) / TBK, nst2 = (p.K2 + TBK - 1) / TBK;
   const int nst = nst1 + nst2;
@@ -724,11 +746,13 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if (warp >= 2) {
       const uint32_t conv0 = mapa_u32(&sm->conv[0], 0);
       const F16Scales sc = rows_scales<F16>(p);
+      PROF_DECL;
       uint32_t it = 0;
       for (int64_t u = pair; u < nunits; u += npairs) {
         const RowsUnit un = rows_unit(p, u, nst);
-        for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_b_stage<F16>(base, sm, conv0, it, sc);
+        for (int st = un.k_begin; st < un.k_end; ++st, ++it) convert_b_stage<F16>(base, sm, conv0, it, sc, pw0, pw1);
       }
+      if (threadIdx.x == 64) PROF_STORE(4);
     } else if (warp == 0 && lane == 0) {
       PROF_DECL;
       tma_prefetch_desc(&tmA1);

@@ -63,8 +63,8 @@ enum gpp_scalar_slot {
 
 int gpp_version(void);
 const char* gpp_last_error(void);
-/* Which GEMM engine the library was built with: "tcgen05-tf32+2xf16" (3-term split: TF32 main term + two fp16
- * correction terms) or "simt-fp32". */
+/* Which GEMM engine the library was built with: "tcgen05-3xf16" (3-term split of every fp32 product on the fp16 tensor
+ * pipe; the Q-space block GEMMs keep a TF32 main term) or "simt-fp32". */
 const char* gpp_gemm_engine(void);
 /* Number of kernels this library has launched in the process so far (bench.py reports the delta). */
 uint64_t gpp_launch_count(void);

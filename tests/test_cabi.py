@@ -45,7 +45,7 @@ def test_library_is_sm100a_and_torch_free(lib):
 def test_version_engine_and_launch_counter(lib):
     from gppvae_b200 import _lib
     assert lib.gpp_version() >= 100
-    assert _lib.gemm_engine() in ("simt-fp32", "tcgen05-tf32+2xf16")
+    assert _lib.gemm_engine() in ("simt-fp32", "tcgen05-3xf16")
     assert _lib.launch_count() >= 0
 
 

@@ -44,7 +44,7 @@ def _golden_V(g, dev):
 def test_library_is_the_cuda_one():
     from gppvae_b200 import _lib
     assert _lib.load().gpp_version() >= 100
-    assert _lib.gemm_engine() in ("simt-fp32", "tcgen05-tf32+2xf16")
+    assert _lib.gemm_engine() in ("simt-fp32", "tcgen05-3xf16")
 
 
 def test_vmodel_forward_backward(golden, dev):
