@@ -231,16 +231,17 @@ template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- pieces shared by the two kernels ----------------------------------------------------------------------
-// F16: the raw tiles are read by the converter warps only (the MMAs take all operands from the fp16 planes / TMEM), so a
-// raw slot is handed back to the TMA producer by its six local converter warps as soon as they hold it in registers --
-// not by the MMA commit, which in the tf32 split keeps a slot for the whole correction-terms-first group.
+// Raw slots are handed back to the TMA producer by the MMA commit in both splits.  (Releasing them from the converter
+// warps as soon as the tile is in registers -- possible in the fp16 split, whose MMAs never read the raw tile -- was
+// measured: no gain, the kernel is bound by the L2 -> shared-memory stream, and an intermittent 6e-4 error in the
+// Gram tiles, i.e. the arrive does not order the converters' outstanding shared-memory loads before the next TMA write.)
 template <bool F16>
 __device__ __forceinline__ TcShared* tc_prologue(uint8_t* base, uint32_t& tmem) {
   TcShared* sm = reinterpret_cast<TcShared*>(base + kRaw * kRawBytes + kLo * kBBytes);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRaw; ++s) {
       mbar_init(&sm->full[s], 1);
-      mbar_init(&sm->empty[s], F16 ? 6 : 1);
+      mbar_init(&sm->empty[s], 1);
     }
     for (int s = 0; s < kLo; ++s) {
       mbar_init(&sm->conv[s], 12);    // (4 A + 2 B converter warps) x 2 CTAs (used in the leader)
@@ -349,10 +350,7 @@ __device__ __forceinline__ void convert_a_stage(uint8_t* base, TcShared* sm, uin
     a16[c] = F16 ? pack_f16x2((x0 - l0) * sc.a_hi, (x1 - l1) * sc.a_hi) : pack_f16x2(x0 * sc.a_hi, x1 * sc.a_hi);
     a16[TBK / 2 + c] = pack_f16x2(l0 * sc.a_lo, l1 * sc.a_lo);
   }
-  if (F16) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm->empty[s]);   // raw tile consumed (values are in registers)
-  } else {
+  if (!F16) {
 #pragma unroll
     for (int k = 0; k < TBK; ++k) ahi[k] = __float_as_uint(__uint_as_float(ahi[k]) * sc.a32);   // exact
   }
@@ -381,10 +379,6 @@ __device__ __forceinline__ void convert_b_stage(uint8_t* base, TcShared* sm, uin
   float4 bv[kBUnitsB];
 #pragma unroll
   for (int i = 0; i < kBUnitsB; ++i) bv[i] = b_unit_load(braw, w2 * kBUnitsB + i, lane);
-  if (F16) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm->empty[s]);   // raw tile consumed (values are in registers)
-  }
   PROF_WAIT(pw1, mbar_wait(&sm->lo_empty[sl], ((it / kLo) & 1) ^ 1));
   const uint32_t bplane = smem_u32(base + kRaw * kRawBytes + sl * kBBytes);
 #pragma unroll
@@ -440,7 +434,7 @@ __device__ __forceinline__ void issue_group(uint8_t* base, TcShared* sm, uint32_
       for (int kk = 0; kk < TBK / 8; ++kk)
         umma_tf32_pair_ts(d, a_hi + kk * 8, umma_desc(b_hi + kk * 1024, TBK * 128, 512, kLayoutSw128Base32), idesc, 1);
     }
-    if (!F16) umma_commit_pair(&sm->empty[s], 3);   // raw tile (tf32 split), fp16 planes and A slot are free in both CTAs
+    umma_commit_pair(&sm->empty[s], 3);       // raw tile, fp16 planes and A slot are free in both CTAs
     umma_commit_pair(&sm->lo_empty[sl], 3);
   }
   if (win_ends(g, ngroups)) {
