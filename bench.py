@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 from gppvae_b200.synth import CONFIGS, make_problem  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of tc_pass1_kernel per launch, from profiles/ (ncu --set full, 1 GPU)
-TRAFFIC = {("c3", 1): 42.031754e9 + 0.435834e9, ("c2", 1): 562.136576e6 + 65.065472e6}
+TRAFFIC = {("c3", 1): 42.348001e9 + 0.451665e9, ("c2", 1): 562.136576e6 + 65.065472e6}
 
 METRIC = "gp_term_samples_per_s"
 UNIT = "samples/s"
@@ -385,7 +385,7 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "pass 1: V^T[V|Z] (tc_pass1_kernel + tc_reduce_kernel + tc_mirror_kernel)",
                      "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                      "frac": (achieved / tf32_peak) if achieved else None, "traffic": traffic,
-                     "traffic_source": "ncu --set full, profiles/r01_pass1_c3_aligned_ncu_full.txt / r01_c2_final_ncu_full.txt"
+                     "traffic_source": "ncu --set full, profiles/r01_pass1_c3_f16_ncu_full.txt / r01_c2_final_ncu_full.txt"
                                        if traffic else None,
                      "algorithmic_bytes_per_launch": float(n) * (4 * Q + 4 * L) + 4.0 * Q * (Q + L),
                      "peak_source": f"{pk['source']} bf16_tflops_sustained / 2 (dense TF32), k=1 algorithmic flops",
