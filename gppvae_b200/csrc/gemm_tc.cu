@@ -1,5 +1,5 @@
 // Pass 1, pass 2, Vb and the Q-space block GEMMs on the 5th-generation tensor cores, fp32-accurate through a 3-term
-// operand split  a.b ~= hi(a).hi(b) + a.lo(b) + lo(a).b,  on CTA PAIRS, with the M operand in TENSOR MEMORY.
+// operand split  a.b ~= hi(a).hi(b) + hi(a).lo(b) + lo(a).hi(b),  on CTA PAIRS, with the M operand in TENSOR MEMORY.
 //
 // Every GEMM tile is 256 x 256 and belongs to a cluster of two CTAs (tcgen05 cta_group::2): each CTA stages ITS 128
 // rows of the M operand (A) and ITS 128 columns of the N operand (B); the leader CTA issues M = 256, N = 256 MMAs whose
@@ -7,28 +7,24 @@
 // receives its 128 accumulator rows.
 //
 //   pass 1:  D = sum_k A[k, m]^T B[k, n]   A = V[:, 256 tm ..], B = V[:, 256 tn ..] or X[:, 256 j ..]
-//            both operands are row-major with the contraction over ROWS.  B is an MN-major UMMA operand; for tf32
-//            the only MN-major layout is SWIZZLE_128B_BASE32B (atom = 32 floats x 4 k-rows, 32-byte chunks XORed with
-//            row % 4), which is what a TMA box {32 floats, BK rows} with SWIZZLE_128B_ATOM_32B writes:
-//            LBO = BK * 128 B between 32-float column groups, SBO = 512 B between 4-row k-groups, 1 KB per K = 8.
-//            A lands in shared memory the same way and is TRANSPOSED into TMEM by the converter warps (thread m reads
-//            column m of the tile: conflict-free, one 128-byte row per warp and k).
+//            both operands are row-major with the contraction over ROWS.  The raw fp32 tiles are written by a TMA box
+//            {32 floats, BK rows} with SWIZZLE_128B_ATOM_32B (atom = 32 floats x 4 k-rows, 32-byte chunks XORed with
+//            row % 4) -- for tf32 the only MN-major UMMA layout (LBO = BK * 128 B between 32-float column groups,
+//            SBO = 512 B between 4-row k-groups, 1 KB per K = 8), which the wide-range variant feeds to the tensor
+//            core as it landed.  A is TRANSPOSED into TMEM by the converter warps (thread m reads column m of the
+//            tile: conflict-free, one 128-byte row per warp and k).
 //   rows  :  D = sum_k [A1 | A2][row, k] B[k, col]   (pass 2: A1 = V, B = W; Vb: A1 = V, A2 = Xb, B = [rL Binv; -W^T])
 //            A lands K-major: TMA box {16 floats, 128 rows} with SWIZZLE_64B; thread m reads its row (4 x 128 bit).
 //
-// The three terms per 16-row stage (hardware facts measured on B200, experiments/tc/exp1_gram.cu: kind::tf32
-// TRUNCATES fp32 operands, and the TMEM accumulator is rounded toward zero after every MMA):
-//   hi.hi  : two K = 8 kind::tf32 MMAs on the RAW fp32 data (the hardware truncation is the split): A from TMEM,
-//            B = the TMA tile as it landed;
-//   a.lo(b), lo(a).b : lo(x) = x - trunc_tf32(x) is exact in fp32 and has <= 13 significant bits, the other factor
-//            needs only ~11 bits, so each correction term is ONE K = 16 kind::f16 MMA on fp16 operands.  Every fp16
-//            factor is normalised by a power of two taken from its own operand's magnitude (absmax_bits_kernel, see
-//            F16Scales), which makes the scheme independent of the units of A and B; the common factor 2^g that
-//            the two terms then carry is also given to the hi.hi term (its A operand is written to TMEM as a 2^g,
-//            exact) and removed by the drain warps (exact).  Half the tensor-pipe time of two tf32 MMAs, and more
-//            accurate than tf32 correction terms (fp16 rounds a to nearest where tf32 truncates it): G, C against
-//            fp64 1.0-1.4e-7 of max|G| for V, Z scaled anywhere between 1e-6 and 3e5 (the exact-fp32 SIMT engine:
-//            0.9-2.5e-7).
+// The three terms per 16-row stage come in two variants (template parameter F16; see the comment at F16Scales).
+// Hardware facts measured on B200 (experiments/tc/exp1_gram.cu): kind::tf32 TRUNCATES fp32 operands, and the TMEM
+// accumulator is rounded toward zero after every MMA.
+//   F16 = true (data passes): hi(x) = x rounded to 11 significant bits, lo(x) = x - hi(x); all three terms are ONE
+//            K = 16 kind::f16 MMA each, on fp16 operands that carry one common power-of-two scale per operand
+//            (absmax_bits_kernel): A hi / lo from TMEM, B hi / lo from two fp16 planes in shared memory.
+//   F16 = false (Q-space block GEMMs, wide dynamic range): hi.hi as two K = 8 kind::tf32 MMAs on the RAW fp32 data
+//            (the hardware truncation is the split; B = the TMA tile as it landed), the correction terms a.lo(b) and
+//            lo(a).b as one K = 16 kind::f16 MMA each with their own scale.
 //   Accumulation in TMEM is limited to WINDOWS of 4 stages (64 k-rows); inside a window ALL correction terms are
 //   issued first, into the still-small accumulator, the hi.hi terms last (a correction term added to a large
 //   accumulator is truncated at the accumulator's ulp: measured 1.5e-6 with 2-stage groups in an 8-stage window).
@@ -37,8 +33,8 @@
 // Why A lives in TMEM.  With both operands in shared memory a 16-row stage cost, per CTA, 48 KB of MMA operand reads
 // + 32 KB of converter traffic + 16 KB of TMA writes = 848 shared-memory wavefronts against 768 tensor-pipe cycles:
 // the first pair kernel was shared-memory-bandwidth bound.  Now: 16 KB of B reads + 24 KB converter + 16 KB TMA.
-// TMEM map (512 columns): [0, 256) the accumulator tile; [256, 512) ring of 8 A slots: 16 columns raw fp32 (hi) +
-// 8 columns fp16 pairs (a 2^-6) + 8 columns fp16 pairs (lo 2^6) per stage.
+// TMEM map (512 columns): [0, 256) the accumulator tile; [256, 512) ring of 8 A slots of 32 columns per stage: 8 columns
+// of fp16 hi pairs + 8 of lo pairs (F16), or 16 columns a 2^g in fp32 + 8 + 8 columns of fp16 pairs (wide-range).
 // (Measured and dropped: two staggered 128-column half accumulators -- an N = 128 MMA with A from TMEM takes ~117
 //  cycles, not 64; separate rings for the raw A and B tiles; L2 prefetch of later stages -- 30 % SLOWER; k-splits from
 //  2 k to 55 k rows -- no effect.  Kept: the per-wave alignment of the producers, see the producer loop of pass 1.)
@@ -65,10 +61,10 @@ using namespace tc;
 namespace {
 
 #ifndef GPP_TC_RAW
-#define GPP_TC_RAW 10    // raw tiles in flight: TMA -> converter -> MMA (B hi is read from them)
+#define GPP_TC_RAW 10    // raw tiles in flight: TMA -> converter -> MMA (wide-range variant: B hi is read from them)
 #endif
 #ifndef GPP_TC_LO
-#define GPP_TC_LO 8      // lo slots in flight (B lo in shared memory + A hi/lo in TMEM): converter -> MMA
+#define GPP_TC_LO 8      // converted slots in flight (fp16 planes of B in shared memory + A slot in TMEM): converter -> MMA
 #endif
 constexpr int TM = 256, TN = 256;   // tile of a CTA pair
 constexpr int HM = 128, HN = 128;   // what one CTA stages of it
@@ -90,12 +86,8 @@ constexpr int kSmemBytes = kRaw * kRawBytes + kLo * kBBytes + 1024 /*align*/ + 5
 #ifndef GPP_TC_F16_SBO
 #define GPP_TC_F16_SBO 1024
 #endif
-// Scales of the split (all exact powers of two).  With eA, eB the binary exponents of max|A|, max|B| (measured on the
-// device by absmax_bits_kernel; 0 when unknown) every fp16 factor is normalised by its own operand's magnitude,
-//   a.lo(b)  ->  (a 2^-eA) . (lo(b) 2^(11 - eB))        lo(a).b  ->  (lo(a) 2^(11 - eA)) . (b 2^-eB)
-// (lo(x) <= 2^-10 |x|, hence the extra 2^11), so all four sit around 2^-4 with maxima near 1 whatever the units of
-// A and B are.  Both terms come out scaled by 2^g, g = 11 - eA - eB; the hi.hi term is brought to the same scale by
-// writing a 2^g (exact) as its A operand, and the drain warps multiply the finished sums by 2^-g (exact).
+// Scales of the split (all exact powers of two), from eA, eB = the binary exponents of max|A|, max|B| (measured on the
+// device by absmax_bits_kernel; 0 when unknown).
 // Two splits live side by side, chosen per launch (template parameter F16):
 //   F16 = true   all three terms on the fp16 pipe (three K = 16 fp16 MMAs per stage, 1.5 TF32-pass equivalents): the
 //                large data passes (V^T [V | Z], Z - V W, Vb, the structured route's products);
