@@ -1,5 +1,5 @@
 """Coherent (same-sign) accumulation bias of the tensor-core Gram / cross product: mean signed relative error of
-V^T [V | Z] against float64 on all-positive data of several distributions.  Calibrates / checks kRzComp (gemm_tc.cu)."""
+V^T [V | Z] against float64 on all-positive data of several distributions.  Background for kDiagComp (gemm_tc.cu); see also smoke_diag.py."""
 import os, sys
 sys.path.insert(0, ".")
 lib = os.environ.get("GPPVAE_LIB")

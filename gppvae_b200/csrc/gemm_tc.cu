@@ -119,13 +119,21 @@ __device__ __forceinline__ float hi11(uint32_t bits) {
 // fp16 maximum for rows the magnitude sample did not see, and a remainder that stays a normal fp16 number for every
 // element above 2^-10 of the maximum (below that the error is bounded by 2^-32 of the maximum).
 constexpr int kF16Top = 7;
-// The tensor core adds into its fp32 accumulator with truncation, which on coherent (same-sign) sums is a relative bias
+// The tensor core adds into its fp32 accumulator with truncation.  On coherent (same-sign) sums that is a relative bias
 // of -1.4e-7 ... -3.1e-7 for this window schedule, depending on the spread of the magnitudes (experiments/bench/
-// bias_cal.py; the tf32 split measures -0.4e-7 ... -2.8e-7, part of it hidden by its over-counted lo.lo term).  The
-// fp16 split scales the finished sums by 1 + kRzComp in the drain (one fused multiply-add, rounded to nearest), which
-// centres it: +0.5e-7 ... -1.1e-7 on the same data.
-template <bool F16>
-struct RzComp { static constexpr float value = F16 ? 2.0e-7f : 0.f; };
+// bias_cal.py; the tf32 split measures -0.4e-7 ... -2.8e-7, part of it hidden by its over-counted lo.lo term); on
+// mixed-sign sums it is about half of that.  A common relative bias of G and V^T Z cancels in W = r B^-1 C; what does
+// not cancel is the DIFFERENCE between the entries that are same-sign by construction -- the diagonal of the Gram
+// matrix, G_ii = sum v^2 -- and the rest: a diagonal that is 1e-7 smaller than its surroundings makes B too small and W
+// too large, which the NLL sees amplified (experiments/bench/smoke_diag.py, six shapes: NLL error -0.9e-6 ... -6e-6
+// without a correction, +1.3e-6 ... +6.5e-6 with the full coherent bias 2.2e-7 added back to the diagonal, zero at
+// 0.9e-7 ... 1.2e-7 in all six).  The fp16 split therefore scales the diagonal entries of G by 1 + kDiagComp in the
+// fp64 reduction of pass 1.  (Scaling every finished sum in the drain instead -- which centres all-positive test
+// matrices -- over-corrects the mixed-sign products of pass 2: NLL error -3.9e-6 per 1e-7 of compensation.)
+#ifndef GPP_TC_DIAGCOMP
+#define GPP_TC_DIAGCOMP 1.1e-7
+#endif
+constexpr double kDiagComp = GPP_TC_DIAGCOMP;
 // tf32 split: each fp16 factor of the correction terms is normalised by its own operand's magnitude,
 //   a.lo(b) -> (a 2^-eA) . (lo(b) 2^(11 - eB))      lo(a).b -> (lo(a) 2^(11 - eA)) . (b 2^-eB)
 // both scaled by 2^g, g = 11 - eA - eB; hi.hi is brought to the same scale by writing a 2^g (exact) as its A operand.
@@ -198,6 +206,7 @@ struct Pass1Params {
   float* G; int64_t ldg;   // V^T V  (not touched when tiles_g == 0)
   float* C; int64_t ldc;   // V^T X
   const double* scal_c;    // when set: C *= scal[V0] / scal[VN]
+  double diag_scale;       // factor applied to the diagonal entries of G in the reduction (1 + kDiagComp, or 1)
   const uint32_t* amax;    // device: [0] bits of max|V|, [1] bits of max|X| (fp16 scales); may be null
   unsigned int* wave_ctr;  // device, zeroed before the launch: producer-units issued so far (wave alignment); may be null
 };
@@ -597,10 +606,7 @@ tc_pass1_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__
                    (size_t)(rank * HM + q * 32 + lane) * TN + cb * 128;
 #pragma unroll
       for (int i = 0; i < 128; i += 4) {
-        constexpr float kc = RzComp<F16>::value;
-        const float y0 = os * acc[i], y1 = os * acc[i + 1], y2 = os * acc[i + 2], y3 = os * acc[i + 3];
-        *reinterpret_cast<float4*>(out + i) =
-            make_float4(fmaf(y0, kc, y0), fmaf(y1, kc, y1), fmaf(y2, kc, y2), fmaf(y3, kc, y3));
+        *reinterpret_cast<float4*>(out + i) = make_float4(os * acc[i], os * acc[i + 1], os * acc[i + 2], os * acc[i + 3]);
       }
     }
     if (threadIdx.x == 256) PROF_STORE(3);
@@ -626,6 +632,13 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(Pass1Params p) {
     for (int s = 0; s < p.splits; ++s) {
       const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * (TM * TN) + r * TN + c4);
       s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+    }
+    if (!is_c && tm == tn) {   // diagonal entries of G: same-sign sums, see kDiagComp
+      const int dc = row0 + r - (col0 + c4);
+      if (dc == 0) s0 *= p.diag_scale;
+      else if (dc == 1) s1 *= p.diag_scale;
+      else if (dc == 2) s2 *= p.diag_scale;
+      else if (dc == 3) s3 *= p.diag_scale;
     }
     float* dst = (is_c ? p.C + (int64_t)(row0 + r) * p.ldc : p.G + (int64_t)(row0 + r) * p.ldg) + col0 + c4;
     *reinterpret_cast<float4*>(dst) =
@@ -815,10 +828,7 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
       for (int g = 0; g < ngroups; ++g) drain_group(sm, tmem, tempty0, g, ngroups, wc, acc, pw0);
 #pragma unroll
-      for (int i = 0; i < 128; ++i) {   // undo the common power-of-two scale of the split (exact), centre the RZ bias
-        const float y = acc[i] * os;
-        acc[i] = fmaf(y, RzComp<F16>::value, y);
-      }
+      for (int i = 0; i < 128; ++i) acc[i] *= os;   // undo the common power-of-two scale of the split (exact)
       // ---- epilogue for this unit: this CTA's 128 rows, this warp's 128 columns
       const int64_t row = rt * TM + rank * HM + q * 32 + lane;
       const int col0 = ct * TN + cb * 128;
@@ -1044,6 +1054,7 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
   }
   if (p.wave_ctr) GPP_CUDA(cudaMemsetAsync(p.wave_ctr, 0, 4, st));
   p.G = G; p.ldg = ldg; p.C = C; p.ldc = ldc; p.scal_c = scal_c;
+  p.diag_scale = wide_range ? 1.0 : 1.0 + kDiagComp;
   CUtensorMap tmV, tmX;
   GPP_TRY(make_map_2d(&tmV, V, n, Q, ldv, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   if (L > 0) GPP_TRY(make_map_2d(&tmX, X, n, L, ldx, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
