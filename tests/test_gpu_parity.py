@@ -425,6 +425,31 @@ def test_qspace_large_against_fp64(dev, Q, L, r):
     assert rel_err(W[:, :L].cpu(), W64.cpu()) < 1e-4
 
 
+@pytest.mark.parametrize("n,p,q,L,lvs,seed", [(1536, 16, 8, 64, (0.4, -0.6), 1), (1536, 16, 8, 64, (0.4, -0.6), 2),
+                                               (4000, 32, 8, 64, (0.0, 0.0), 4), (4000, 32, 8, 128, (1.0, -2.0), 5),
+                                               (20000, 64, 8, 256, (0.4, -0.6), 6)])
+def test_nll_bias_small_shapes(dev, n, p, q, L, lvs, seed):
+    """sum(nll) is the quantity that amplifies a bias of the Gram diagonal against its surroundings (gemm_tc.cu,
+    kDiagComp): without the diagonal compensation these shapes sit at -1e-6 ... -6e-6, with a drain-wide compensation
+    the first one crossed 1e-5.  Graded against the float64 oracle, with a margin to the north-star bound."""
+    import gppvae_b200
+    from gppvae_b200.synth import make_problem
+    from oracle import gp_oracle as O
+    pr = make_problem(n, p, q, L, kind="trained", lvs=lvs, seed=seed)
+    V64 = O.feature_map(pr.x0.double(), pr.v0.double(), pr.d, pr.w)
+    oXb, _, _, onll = O.taylor_coeff(pr.Z.double(), [V64], pr.lvs.double())
+    vm = gppvae_b200.Vmodel(pr.x0.shape[0], q, p, q).to(dev)
+    gp = gppvae_b200.GP().to(dev)
+    with torch.no_grad():
+        vm.x0.copy_(pr.x0.to(dev)); vm.v0.copy_(pr.v0.to(dev)); gp.lvs.copy_(pr.lvs.to(dev))
+        V = vm(pr.d.to(dev), pr.w.to(dev))
+    Xb, _, _, nll = gp.taylor_coeff(pr.Z.to(dev), [V], need_vb=False)
+    e_nll = (nll.double().sum().item() - onll.sum().item()) / abs(onll.sum().item())
+    print(f"[n={n} Q={p * q} L={L} lvs={lvs}] rel NLL err {e_nll:+.2e}  Xb {rel_err(Xb.cpu(), oXb):.2e}")
+    assert abs(e_nll) < 3e-6
+    assert rel_err(Xb.cpu(), oXb) < GRAD_TOL
+
+
 @pytest.mark.parametrize("Q,L,r", [(1600, 132, 50.0), (2048, 256, 400.0)])
 def test_qspace_outer_block_cholesky(dev, monkeypatch, Q, L, r):
     """From Q = 6144 up the Cholesky works in 256-wide outer blocks whose trailing updates are rank-256 products on the
