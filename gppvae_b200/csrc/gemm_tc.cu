@@ -927,16 +927,18 @@ int make_map_2d(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, in
   return GPP_OK;
 }
 
-// Record the bit pattern of max|X| over (a sample of) X in *slot (zeroed here); the kernels derive the fp16 scales of
-// the correction terms from it.  Large row operands are sampled (first 8192 rows): the scale only centres the fp16
-// range, it does not affect correctness.
+// Record the bit pattern of max|X| over (a sample of) X in *slot (zeroed here); the kernels derive the power-of-two
+// scales of the fp16 operands from it.  Large row operands are sampled: about 8192 rows at a constant stride over the
+// whole matrix (not its head -- rows are often sorted by object).  The fp16 split leaves 2^8 of headroom above the
+// sampled maximum before an element saturates (kF16Top), the tf32 split 2^16.
 constexpr int64_t kAbsmaxSampleRows = 8192;
 int launch_absmax(const float* X, int64_t ld, int64_t rows, int cols, uint32_t* slot, cudaStream_t st) {
   GPP_CUDA(cudaMemsetAsync(slot, 0, 4, st));
-  if (rows > kAbsmaxSampleRows) rows = kAbsmaxSampleRows;
   if (rows <= 0 || cols < 4) return GPP_OK;
-  const int grid = (int)(rows < 592 ? rows : 592);
-  absmax_bits_kernel<<<grid, 256, 0, st>>>(X, ld, rows, cols, slot);
+  const int64_t stride = rows > kAbsmaxSampleRows ? rows / kAbsmaxSampleRows : 1;
+  const int64_t sampled = (rows + stride - 1) / stride;
+  const int grid = (int)(sampled < 592 ? sampled : 592);
+  absmax_bits_kernel<<<grid, 256, 0, st>>>(X, ld * stride, sampled, cols, slot);
   GPP_LAUNCH_CHECK();
   return GPP_OK;
 }
