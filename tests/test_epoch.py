@@ -86,3 +86,86 @@ def test_epoch_against_reference_sequence(lazy):
         assert rel_err(gp.lvs.detach().cpu(), g["after.gp.lvs"]) < 1e-4
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
+
+
+# ---- the same epoch on CPU through the test-only stand-in engine (tests/fake_engine.py): covers the HOST logic of
+# epoch.py -- sequencing, minibatch indexing, the lazy route, and (world_size 2, gloo) the row sharding of the images
+# with its single all-reduce of the gradients -- against the same golden vectors of the unmodified reference.
+def _cpu_epoch(g, rows, lazy, group=None, n_total=None):
+    import gppvae_b200
+    from gppvae_b200.epoch import train_epoch
+    vae = _vae(g, torch.float32)
+    vm = gppvae_b200.Vmodel(int(g["P"]), int(g["Q"]), int(g["p"]), int(g["Q"]))
+    gp = gppvae_b200.GP()
+    if group is not None:
+        gp.shard_rows(group)
+    with torch.no_grad():
+        vm.x0.copy_(torch.as_tensor(g["init.vm.x0"])); vm.v0.copy_(torch.as_tensor(g["init.vm.v0"]))
+        gp.lvs.copy_(torch.as_tensor(g["init.gp.lvs"]))
+    Y, Eps, D, W = (torch.as_tensor(g[k])[rows] for k in ("Y", "Eps", "D", "W"))
+    bs = int(g["bs"])
+    # the reference's minibatch order, restricted to this rank's rows and renumbered locally
+    order = torch.as_tensor(g["order"])
+    local = {int(r): i for i, r in enumerate(rows.tolist())}
+    mine = torch.tensor([local[int(r)] for r in order.tolist() if int(r) in local])
+    batches = [mine[a:a + bs] for a in range(0, mine.numel(), bs)]
+    vae_opt = torch.optim.Adam(vae.parameters(), lr=2e-4)
+    gp_opt = torch.optim.Adam(list(vm.parameters()) + list(gp.parameters()), lr=1e-3)
+    rv = train_epoch(vae, vm, gp, Y, D, W, vae_opt, gp_opt, bs=bs, eps=Eps, batches=batches, lazy=lazy, step=False,
+                     group=group, n_total=n_total)
+    grads = {"vae." + n: p.grad.clone() for n, p in vae.named_parameters() if p.grad is not None}
+    grads.update({"vm.x0": vm.x0.grad.clone(), "vm.v0": vm.v0.grad.clone(), "gp.lvs": gp.lvs.grad.clone()})
+    return rv, grads
+
+
+def _check_epoch(g, rv, grads):
+    for key in ("mse", "recon_term", "pen_term", "gp_nll", "loss"):
+        assert abs(rv[key] - float(g["out." + key])) < 2e-4 * abs(float(g["out." + key])), key
+    for name, gr in grads.items():
+        assert rel_err(gr, g["grad." + name]) < 2e-3, name
+
+
+@pytest.mark.parametrize("lazy", [True, False])
+def test_epoch_host_logic_cpu(monkeypatch, lazy):
+    import fake_engine
+    fake_engine.install(monkeypatch)
+    g = _golden()
+    rv, grads = _cpu_epoch(g, torch.arange(g["Y"].shape[0]), lazy)
+    _check_epoch(g, rv, grads)
+
+
+def _epoch_shard_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from _pytest.monkeypatch import MonkeyPatch
+    import fake_engine
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mpch = MonkeyPatch()
+    fake_engine.install(mpch)
+    try:
+        torch.set_num_threads(2)
+        g = _golden()
+        n = g["Y"].shape[0]
+        cut = (n * 3) // 5                                   # deliberately unequal shards
+        rows = torch.arange(0, cut) if rank == 0 else torch.arange(cut, n)
+        rv, grads = _cpu_epoch(g, rows, True, group=dist.group.WORLD, n_total=n)
+        torch.save(dict(rv=rv, grads=grads), os.path.join(out, f"r{rank}.pt"))
+    finally:
+        mpch.undo()
+        dist.destroy_process_group()
+
+
+def test_epoch_row_sharding_world2_gloo(tmp_path):
+    """Two ranks hold 24 and 16 of the 40 images: every rank encodes / decodes its own images, the GP term all-reduces
+    its Q-space partials, gradients are all-reduced once -- metrics and gradients equal the unsharded reference's on
+    both ranks."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_epoch_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g = _golden()
+    r0 = torch.load(os.path.join(tmp_path, "r0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "r1.pt"))
+    for r in (r0, r1):
+        _check_epoch(g, r["rv"], r["grads"])
+    for name in r0["grads"]:
+        assert torch.equal(r0["grads"][name], r1["grads"][name]), name
