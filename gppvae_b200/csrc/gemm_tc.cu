@@ -122,7 +122,7 @@ constexpr int kF16Top = 7;
 // The tensor core adds into its fp32 accumulator with truncation.  On coherent (same-sign) sums that is a relative bias
 // of -1.4e-7 ... -3.1e-7 for this window schedule, depending on the spread of the magnitudes (experiments/bench/
 // bias_cal.py; the tf32 split measures -0.4e-7 ... -2.8e-7, part of it hidden by its over-counted lo.lo term); on
-// mixed-sign sums it is about half of that.  A common relative bias of G and V^T Z cancels in W = r B^-1 C; what does
+// mixed-sign sums it is smaller (the NLL experiment below is consistent with about half).  A common relative bias of G and V^T Z cancels in W = r B^-1 C; what does
 // not cancel is the DIFFERENCE between the entries that are same-sign by construction -- the diagonal of the Gram
 // matrix, G_ii = sum v^2 -- and the rest: a diagonal that is 1e-7 smaller than its surroundings makes B too small and W
 // too large, which the NLL sees amplified (experiments/bench/smoke_diag.py, six shapes: NLL error -0.9e-6 ... -6e-6
