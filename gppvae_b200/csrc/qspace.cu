@@ -656,7 +656,7 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
   // 256-deep contraction does not amortise the tensor-core kernel's pipeline fill and epilogue) do not.  Hence the switch.
   constexpr int kOuter = 4;
   const char* min_q_env = getenv("GPP_CHOL_OUTER_MIN_Q");             // tests force the outer scheme at small Q
-  const bool outer = Qp >= (min_q_env ? atoi(min_q_env) : kOuterCholMinQ);
+  const bool outer = Qp >= (min_q_env ? atoi(min_q_env) : kOuterCholMinQ) && tc_blockgemm_supported(512, kOuter * NB, 512);
   for (int j = 0; j < nb; ++j) {
     const int npanel = nb - j;
     const int jj = outer ? j % kOuter : 0;
