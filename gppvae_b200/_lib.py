@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgppvae_b200.so")
 
 GPP_WANT_BINV = 1
+GPP_PLANES_COLSQ, GPP_PLANES_UNIT_BOUND = 1, 2
 # scalar slots (enum gpp_scalar_slot)
 S_V0, S_VN, S_LOGDETB, S_TRBINV, S_WNORM2, S_ROWCONST, S_XB2, S_QUAD, NSCAL = range(9)
 
@@ -52,6 +53,19 @@ _SIGNATURES = {
     "gpp_atb_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "gpp_atb": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, _PF, c_int64, _PF, c_size_t,
                         c_void_p]),
+    "gpp_planes_bytes": (c_size_t, [c_int64, c_int32]),
+    "gpp_split_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "gpp_planes_supported": (c_int, [c_int64, c_int32, c_int32]),
+    "gpp_split_planes": (c_int, [_PF, c_int64, c_int64, c_int32, c_uint32, _PF, c_size_t, _PF, c_size_t, c_void_p]),
+    "gpp_khatri_rao_fwd_planes": (c_int, [_PF, c_int64, c_int32, _PF, c_int64, c_int32, _PF, _PF, c_int64, _PF, c_int64,
+                                          _PF, c_size_t, _PF, c_size_t, c_void_p]),
+    "gpp_gram_planes_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "gpp_gram_vtz_planes": (c_int, [_PF, _PF, c_int64, c_int32, c_int32, c_int32, _PF, c_int64, _PF, c_size_t,
+                                    c_void_p]),
+    "gpp_atb_planes": (c_int, [_PF, _PF, c_int64, c_int32, c_int32, _PF, c_int64, _PF, c_size_t, c_void_p]),
+    "gpp_xb_planes_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "gpp_xb_nll_planes": (c_int, [_PF, _PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, _PF, _PF, c_int64, _PF,
+                                  _PF, c_size_t, c_void_p]),
     "gpp_am": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, c_float, _PF, c_int64, c_void_p]),
     "gpp_kr_slot_sums": (c_int, [_PF, c_int64, _PF, _PF, _PF, c_int64, c_int32, c_int32, c_int32, c_int32, _PF, c_int64,
                                  c_void_p]),

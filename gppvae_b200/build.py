@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgppvae_b200.so")
 STAMP = LIB + ".stamp"
 
-SOURCES = ["api.cu", "featmap.cu", "gemm_simt.cu", "gemm_tc.cu", "qspace.cu", "structured.cu", "taylor.cu"]
+SOURCES = ["api.cu", "featmap.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_planes.cu", "qspace.cu", "structured.cu", "taylor.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

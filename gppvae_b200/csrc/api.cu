@@ -81,6 +81,79 @@ extern "C" int gpp_gram_vtz_simt(const float* V, int64_t ldv, const float* X, in
                    (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ operand planes
+static bool planes_ok(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 255u) == 0; }
+
+extern "C" size_t gpp_planes_bytes(int64_t n, int32_t cols) { return planes_bytes(n, cols); }
+extern "C" size_t gpp_split_workspace_bytes(int64_t n, int32_t cols) { return split_workspace_bytes(n, cols); }
+extern "C" int gpp_planes_supported(int64_t n, int32_t Q, int32_t L) {
+  return pl_pass1_supported(n, Q, L) && pl_rows_supported(n, Q, L > 0 ? L : 64) ? 1 : 0;
+}
+
+extern "C" int gpp_split_planes(const float* X, int64_t ldx, int64_t n, int32_t cols, uint32_t flags, void* planes,
+                                size_t planes_bytes_, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(n >= 0 && cols > 0 && cols % 4 == 0, "split_planes: bad shape n=%lld cols=%d", (long long)n, cols);
+  GPP_REQUIRE(mat_ok(X, ldx, cols), "split_planes: X must be 16-byte aligned with ldx >= cols and ldx %% 4 == 0");
+  GPP_REQUIRE(planes_ok(planes) && planes_bytes_ >= planes_bytes(n, cols),
+              "split_planes: planes buffer must be 256-byte aligned and gpp_planes_bytes() long");
+  return launch_split_planes(X, ldx, n, cols, planes, nullptr, (flags & GPP_PLANES_UNIT_BOUND) ? 1 : 0,
+                             (flags & GPP_PLANES_COLSQ) != 0, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int gpp_khatri_rao_fwd_planes(const float* xn, int64_t P, int32_t p, const float* wn, int64_t nviews,
+                                         int32_t q, const int64_t* d, const int64_t* w, int64_t n, float* V,
+                                         int64_t ldv, void* planes, size_t planes_bytes_, void* workspace,
+                                         size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(xn && wn && d && w && V, "khatri_rao_fwd_planes: null pointer");
+  GPP_REQUIRE(P > 0 && p > 0 && nviews > 0 && q > 0 && n >= 0 && ((int64_t)p * q) % 4 == 0 && (int64_t)p * q < (1 << 30),
+              "khatri_rao_fwd_planes: bad shape");
+  GPP_REQUIRE(mat_ok(V, ldv, (int64_t)p * q), "khatri_rao_fwd_planes: V must be 16-byte aligned with ldv >= p*q");
+  GPP_REQUIRE((q % 4 != 0) || (aligned16(wn)), "khatri_rao_fwd_planes: wn must be 16-byte aligned");
+  GPP_REQUIRE(planes_ok(planes) && planes_bytes_ >= planes_bytes(n, p * q),
+              "khatri_rao_fwd_planes: planes buffer must be 256-byte aligned and gpp_planes_bytes() long");
+  return launch_kr_planes(xn, P, p, wn, nviews, q, d, w, n, V, ldv, planes, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
+extern "C" size_t gpp_gram_planes_workspace_bytes(int64_t n, int32_t Q, int32_t L) {
+  return pl_pass1_workspace_bytes(n, Q, L, false);
+}
+
+extern "C" int gpp_gram_vtz_planes(const void* planesV, const void* planesX, int64_t n, int32_t Q, int32_t L,
+                                   int32_t use_colsq, float* GC, int64_t ldgc, void* workspace, size_t workspace_bytes,
+                                   gpp_stream_t stream) {
+  GPP_REQUIRE(Q > 0 && L >= 0 && Q % 4 == 0 && L % 4 == 0, "gram_vtz_planes: bad shape n=%lld Q=%d L=%d", (long long)n,
+              Q, L);
+  GPP_REQUIRE(pl_pass1_supported(n, Q, L), "gram_vtz_planes: shape below the tensor-core tile (n >= 512, Q >= 128)");
+  GPP_REQUIRE(planes_ok(planesV) && (L == 0 || planes_ok(planesX)), "gram_vtz_planes: planes must be 256-byte aligned");
+  GPP_REQUIRE(mat_ok(GC, ldgc, (int64_t)Q + L), "gram_vtz_planes: GC must be 16-byte aligned with ldgc >= Q + L");
+  return launch_pl_pass1(planesV, planesX, n, Q, L, GC, ldgc, GC + Q, ldgc, use_colsq != 0, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int gpp_atb_planes(const void* planesA, const void* planesB, int64_t n, int32_t ka, int32_t kb, float* out,
+                              int64_t ldo, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(ka > 0 && kb > 0 && ka % 4 == 0 && kb % 4 == 0, "atb_planes: bad shape");
+  GPP_REQUIRE(pl_pass1_supported(n, ka, kb), "atb_planes: shape below the tensor-core tile (n >= 512, ka >= 128)");
+  GPP_REQUIRE(planes_ok(planesA) && planes_ok(planesB) && mat_ok(out, ldo, kb), "atb_planes: bad pointer");
+  return launch_pl_pass1(planesA, planesB, n, ka, kb, nullptr, 0, out, ldo, false, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+
+extern "C" size_t gpp_xb_planes_workspace_bytes(int64_t n, int32_t Q, int32_t L) { return pl_xb_workspace_bytes(n, Q, L); }
+
+extern "C" int gpp_xb_nll_planes(const void* planesV, const float* X, int64_t ldx, const float* W, int64_t ldw,
+                                 int64_t n, int32_t Q, int32_t L, double* scal, float* Xb, int64_t ldxb, float* nll,
+                                 void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(Q > 0 && L > 0 && Q % 4 == 0 && L % 4 == 0, "xb_nll_planes: bad shape");
+  GPP_REQUIRE(pl_rows_supported(n, Q, L), "xb_nll_planes: shape below the tensor-core tile (n >= 512, Q, L >= 64)");
+  GPP_REQUIRE(planes_ok(planesV) && mat_ok(X, ldx, L) && mat_ok(W, ldw, L) && mat_ok(Xb, ldxb, L),
+              "xb_nll_planes: bad pointer / leading dimension");
+  GPP_REQUIRE(scal && nll, "xb_nll_planes: null scal / nll");
+  return launch_pl_xb(planesV, X, ldx, W, ldw, n, Q, L, scal, 0.f, Xb, ldxb, nll, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
 extern "C" size_t gpp_atb_workspace_bytes(int64_t n, int32_t ka, int32_t kb) {
   const size_t a = tn_workspace_bytes(n, ka, 0, kb, 0);
   const size_t b = tc_pass1_supported(n, ka, kb) ? tc_pass1_workspace_bytes(n, ka, kb, true) : 0;

@@ -1,0 +1,762 @@
+// Pass 1 and pass 2 on PRE-SPLIT fp16 operand planes: every fp32 operand x is stored once as two fp16 matrices
+//   hi = x rounded to 11 significant bits,  lo = fp16(x - hi),  both scaled by one power of two per operand
+// (pass1_common.cuh), and  a.b ~= hi(a).hi(b) + hi(a).lo(b) + lo(a).hi(b)  is three kind::f16 tcgen05 MMAs whose
+// operands the TMA writes straight into shared memory, MMA-ready: no converter warps, nothing between the copy engine
+// and the tensor core.  The planes cost the same 4 bytes per element as the fp32 matrix they replace.
+//
+// Why (round-2 measurements on B200, experiments/tc/exp3_f16_planes.cu): a TMA stream is bounded by BOXES per second
+// (3.0 G boxes/s chip-wide whatever the box size: 6.2 TB/s with the 2 KB boxes of the round-1 kernel, 24.6 TB/s with
+// 8 KB boxes), and three SS-form fp16 MMAs per 16 k-rows run at 2.2 PFLOP/s from shared memory alone; with 64-row
+// boxes the stream + MMA pipeline sustains that same rate.  Multicast inside larger clusters bought nothing.
+//
+// Tile = 256 x 256 per CTA pair (cta_group::2), K block = 64 rows = ONE accumulation window (the TMEM accumulator
+// rounds toward zero after every MMA: windows stay 64 k-rows long, inside a window the correction terms are issued
+// first, and finished windows are added in fp32 registers, round-to-nearest, by the drain warps -- as in gemm_tc.cu).
+// TMEM holds TWO accumulators (columns [0,256) and [256,512)): the issuer fills one while the drain warps empty the
+// other.  Shared memory: 3 stages x 64 KB, a stage = 8 boxes {64 halfs, 64 rows} (SWIZZLE_128B):
+//   pass 1:  [Ah g0][Ah g1][Al g0][Al g1][Bh g0][Bh g1][Bl g0][Bl g1]   both operands MN-major (contraction over ROWS)
+//   rows  :  [Ah 128 rows][Al 128 rows][Bh g0][Bh g1][Bl g0][Bl g1]     A K-major boxes {64 halfs, 128 rows}
+// Both CTAs' loads signal the full barrier of the pair LEADER (cta_group::2 form of cp.async.bulk.tensor).
+// Warps: 0 TMA producer, 1 MMA issuer (leader) + TMEM owner, 4-11 drain / epilogue (setmaxnreg 64 / 216).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "pass1_common.cuh"
+#include "tc_common.cuh"
+
+namespace gpp {
+
+using namespace tc;
+
+namespace {
+
+constexpr int PBK = 64;                     // k-rows per stage = one accumulation window
+constexpr int kPlStages = 3;
+constexpr int kBoxBytes = 64 * 128;         // {64 halfs, 64 rows}
+constexpr int kPlStageBytes = 8 * kBoxBytes;
+constexpr int kPlThreads = 384;
+constexpr int kPlSmemBytes = kPlStages * kPlStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(kPlSmemBytes <= 232448, "shared memory budget");
+
+struct PlShared {
+  uint64_t full[kPlStages], empty[kPlStages], tfull[2], tempty[2];
+  uint32_t tmem_base;
+};
+
+// ---- PTX pieces this file adds to tc_common.cuh ---------------------------------------------------------------
+// TMA load whose completion is signalled on the barrier at the same offset in the pair LEADER (address with the peer
+// bit cleared, as CUTLASS' SM100_TMA_2SM_LOAD does).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ PlShared* pl_prologue(uint8_t* base, uint32_t& tmem) {
+  PlShared* sm = reinterpret_cast<PlShared*>(base + kPlStages * kPlStageBytes);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPlStages; ++s) {
+      mbar_init(&sm->full[s], 1);     // the leader's arrive.expect_tx (both CTAs' bytes)
+      mbar_init(&sm->empty[s], 1);    // MMA commit, multicast to both CTAs
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm->tfull[b], 1);    // MMA commit, multicast to both CTAs
+      mbar_init(&sm->tempty[b], 16);  // 8 drain warps x 2 CTAs (used in the leader)
+    }
+    fence_mbar_init();
+  }
+  if ((threadIdx.x >> 5) == 1) tmem_alloc_pair(&sm->tmem_base, 512);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  tmem = sm->tmem_base;
+  return sm;
+}
+
+__device__ __forceinline__ void pl_epilogue(uint32_t tmem) {
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if ((threadIdx.x >> 5) == 1) tmem_dealloc_pair(tmem, 512);
+}
+
+// One window (= one stage, 64 k-rows) of a 256 x 256 tile: correction terms of the four K = 16 steps first (into the
+// still-small accumulator), the hi.hi terms last; then the stage goes back to the producers and the accumulator to the
+// drain warps.  A_KMAJOR: A boxes are {64 halfs of k, 128 rows} (row GEMM), else MN-major like B (pass 1).
+template <bool A_KMAJOR>
+__device__ __forceinline__ void issue_window(uint8_t* base, PlShared* sm, uint32_t tmem, uint32_t it, uint32_t w) {
+  constexpr uint32_t idesc = umma_idesc_f16(kTileM, kTileN, !A_KMAJOR, true);
+  const int s = it % kPlStages, buf = w & 1;
+  mbar_wait_cluster(&sm->tempty[buf], ((w >> 1) & 1) ^ 1);   // drain warps of both CTAs are done with this accumulator
+  mbar_wait(&sm->full[s], (it / kPlStages) & 1);             // both CTAs' boxes have landed
+  tcgen05_fence_after();
+  const uint32_t sb = smem_u32(base + s * kPlStageBytes);
+  const uint32_t d = tmem + buf * 256;
+  const uint32_t ah = sb, al = sb + 2 * kBoxBytes, bh = sb + 4 * kBoxBytes, bl = sb + 6 * kBoxBytes;
+  // MN-major SWIZZLE_128B: 64-column groups kBoxBytes apart (LBO), 8-row k-groups 1 KB apart (SBO), K = 16 -> +2 KB;
+  // K-major SWIZZLE_128B: 8-row groups 1 KB apart (SBO), K = 16 -> +32 B inside the 128-byte row
+  auto adesc = [&](uint32_t a0, int kk) {
+    return A_KMAJOR ? umma_desc(a0 + kk * 32, 16, 1024, kLayoutSw128) : umma_desc(a0 + kk * 2048, kBoxBytes, 1024, kLayoutSw128);
+  };
+  auto bdesc = [&](uint32_t b0, int kk) { return umma_desc(b0 + kk * 2048, kBoxBytes, 1024, kLayoutSw128); };
+#pragma unroll
+  for (int kk = 0; kk < PBK / 16; ++kk) {
+    umma_f16_pair_ss(d, adesc(ah, kk), bdesc(bl, kk), idesc, kk > 0);
+    umma_f16_pair_ss(d, adesc(al, kk), bdesc(bh, kk), idesc, 1);
+  }
+#pragma unroll
+  for (int kk = 0; kk < PBK / 16; ++kk) umma_f16_pair_ss(d, adesc(ah, kk), bdesc(bh, kk), idesc, 1);
+  umma_commit_pair(&sm->empty[s], 3);
+  umma_commit_pair(&sm->tfull[buf], 3);
+}
+
+// Drain warps (4-11): add window w (this CTA's 128 rows x this warp's 128 columns) into registers.
+__device__ __forceinline__ void drain_window(PlShared* sm, uint32_t tmem, uint32_t tempty0_leader, uint32_t w,
+                                             float (&acc)[128]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int buf = w & 1;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const int cb = (warp - 4) >> 2;
+  mbar_wait(&sm->tfull[buf], (w >> 1) & 1);
+  tcgen05_fence_after();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float v[32];
+    tmem_ld_32x32(tmem + lane_addr + buf * 256 + cb * 128 + c * 32, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
+  }
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(tempty0_leader + 8u * buf);
+}
+
+// =====================================================================================================
+// Pass 1:  GC = V^T [V | X] from the planes of V and X.
+// =====================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPlThreads, 1)
+pl_pass1_kernel(const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+                const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl, Pass1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  uint32_t tmem;
+  PlShared* sm = pl_prologue(base, tmem);
+  const int nunits = p.tiles * p.splits;
+
+  if (warp < 4) {
+    setmaxnreg_dec<64>();
+    if (warp == 0 && lane == 0) {
+      // ===================================================== TMA producer (this CTA's halves of A and B)
+      tma_prefetch_desc(&tmVh); tma_prefetch_desc(&tmVl); tma_prefetch_desc(&tmXh); tma_prefetch_desc(&tmXl);
+      const uint32_t full0 = smem_u32(&sm->full[0]) & 0xFEFFFFFFu;   // the leader's barrier
+      uint32_t it = 0;
+      bool wave_sync = p.wave_ctr != nullptr;
+      for (int u = pair; u < nunits; u += npairs) {
+        // Wave alignment (a hint, not a dependency; see gemm_tc.cu): no producer starts the loads of wave w before every
+        // producer has issued all loads of wave w - 1, so the pairs of a wave read the same rows of V while L2 holds them.
+        if (wave_sync && u >= npairs) {
+          const unsigned int target = 2u * (unsigned int)min((u / npairs) * npairs, nunits);
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile unsigned int*>(p.wave_ctr) < target) {
+            if (clock64() - t0 > 4000000ll) {
+              wave_sync = false;
+              break;
+            }
+          }
+        }
+        const int split = u / p.tiles, tile = u - split * p.tiles;   // consecutive pairs share a k-range (L2 reuse)
+        int tm, tn;
+        bool is_c;
+        decode_tile(p, tile, tm, tn, is_c);
+        const int64_t r0 = (int64_t)split * p.rows_per_split;
+        const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+        const int nst = (int)((r1 - r0 + PBK - 1) / PBK);
+        const CUtensorMap* mbh = is_c ? &tmXh : &tmVh;
+        const CUtensorMap* mbl = is_c ? &tmXl : &tmVl;
+        const int acol = tm * kTileM + (int)rank * 128, bcol = tn * kTileN + (int)rank * 128;
+        for (int st = 0; st < nst; ++st, ++it) {
+          const int s = it % kPlStages;
+          mbar_wait(&sm->empty[s], ((it / kPlStages) & 1) ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&sm->full[s], 2 * kPlStageBytes);
+          const uint32_t dst = smem_u32(base + s * kPlStageBytes), bar = full0 + 8u * s;
+          const int row = (int)(r0 + (int64_t)st * PBK);
+          tma_load_2d_pair(dst + 0 * kBoxBytes, &tmVh, acol, row, bar);
+          tma_load_2d_pair(dst + 1 * kBoxBytes, &tmVh, acol + 64, row, bar);
+          tma_load_2d_pair(dst + 2 * kBoxBytes, &tmVl, acol, row, bar);
+          tma_load_2d_pair(dst + 3 * kBoxBytes, &tmVl, acol + 64, row, bar);
+          tma_load_2d_pair(dst + 4 * kBoxBytes, mbh, bcol, row, bar);
+          tma_load_2d_pair(dst + 5 * kBoxBytes, mbh, bcol + 64, row, bar);
+          tma_load_2d_pair(dst + 6 * kBoxBytes, mbl, bcol, row, bar);
+          tma_load_2d_pair(dst + 7 * kBoxBytes, mbl, bcol + 64, row, bar);
+        }
+        if (p.wave_ctr) atomicAdd(p.wave_ctr, 1u);
+      }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      // ===================================================== MMA issuer (leader CTA)
+      uint32_t it = 0;
+      for (int u = pair; u < nunits; u += npairs) {
+        const int split = u / p.tiles;
+        const int64_t r0 = (int64_t)split * p.rows_per_split;
+        const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+        const int nst = (int)((r1 - r0 + PBK - 1) / PBK);
+        for (int st = 0; st < nst; ++st, ++it) issue_window<false>(base, sm, tmem, it, it);
+      }
+    }
+  } else {
+    // ======================================================= drain warps: TMEM windows -> fp32 registers -> partial tile
+    setmaxnreg_inc<216>();
+    const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
+    const int q = warp & 3, cb = (warp - 4) >> 2;
+    const int eV = exp_of_bits(p.amax), eX = exp_of_bits(p.amax_x);
+    const float out_g = exp2f((float)(2 * eV - 2 * kF16Top)), out_c = exp2f((float)(eV + eX - 2 * kF16Top));
+    uint32_t w = 0;
+    for (int u = pair; u < nunits; u += npairs) {
+      const int split = u / p.tiles, tile = u - split * p.tiles;
+      const int64_t r0 = (int64_t)split * p.rows_per_split;
+      const int64_t r1 = min(p.n, r0 + p.rows_per_split);
+      const int nst = (int)((r1 - r0 + PBK - 1) / PBK);
+      float acc[128];
+#pragma unroll
+      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      for (int st = 0; st < nst; ++st, ++w) drain_window(sm, tmem, tempty0, w, acc);
+      const float os = tile < p.tiles_g ? out_g : out_c;   // undo the common power-of-two scale of the split (exact)
+      float* out = p.partial + ((size_t)tile * p.splits + split) * (size_t)(kTileM * kTileN) +
+                   (size_t)(rank * 128 + q * 32 + lane) * kTileN + cb * 128;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4)
+        *reinterpret_cast<float4*>(out + i) = make_float4(os * acc[i], os * acc[i + 1], os * acc[i + 2], os * acc[i + 3]);
+    }
+  }
+  pl_epilogue(tmem);
+}
+
+// =====================================================================================================
+// Row GEMM:  D(256 rows x 256 cols per pair) = sum_k [A1 | A2][row, k] * B[k, col]   (all operands as planes)
+//   mode 0 (pass 2): out = alpha (X - D), per-row quad partials and sum out^2 partials;  mode 1 (Vb): out = alpha D
+// =====================================================================================================
+struct PlRowsParams {
+  int64_t n;
+  int K1, K2;          // contraction lengths of A1 and A2 (K2 may be 0); B has K1 + K2 rows
+  int ncols;
+  int col_tiles;
+  int64_t row_tiles;
+  int mode;
+  const uint32_t* amax_a1; const uint32_t* amax_a2; const uint32_t* amax_b;
+  const float* X; int64_t ldx;
+  float* out; int64_t ldo;
+  const double* scal;  // mode 0: alpha = 1 / scal[VN] when set, else alpha_host
+  float alpha_host;
+  float* quad_part;    // [col_tiles * 2][n]
+  double* xb2_part;    // [units * 16]
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPlThreads, 1)
+pl_rows_kernel(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
+               const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, PlRowsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  uint32_t tmem;
+  PlShared* sm = pl_prologue(base, tmem);
+  const int64_t nunits = p.row_tiles * p.col_tiles;
+  const int nst1 = (p.K1 + PBK - 1) / PBK, nst2 = (p.K2 + PBK - 1) / PBK;
+  const int nst = nst1 + nst2;
+
+  if (warp < 4) {
+    setmaxnreg_dec<64>();
+    if (warp == 0 && lane == 0) {
+      tma_prefetch_desc(&tmA1h); tma_prefetch_desc(&tmA1l); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
+      const uint32_t full0 = smem_u32(&sm->full[0]) & 0xFEFFFFFFu;
+      uint32_t it = 0;
+      for (int64_t u = pair; u < nunits; u += npairs) {
+        const int64_t rt = u / p.col_tiles;
+        const int ct = (int)(u - rt * p.col_tiles);
+        const int row = (int)(rt * kTileM) + (int)rank * 128;
+        const int bcol = ct * kTileN + (int)rank * 128;
+        for (int st = 0; st < nst; ++st, ++it) {
+          const int s = it % kPlStages;
+          mbar_wait(&sm->empty[s], ((it / kPlStages) & 1) ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&sm->full[s], 2 * kPlStageBytes);
+          const uint32_t dst = smem_u32(base + s * kPlStageBytes), bar = full0 + 8u * s;
+          int kb;   // row of B where this k-block starts
+          if (st < nst1) {
+            tma_load_2d_pair(dst, &tmA1h, st * PBK, row, bar);
+            tma_load_2d_pair(dst + 2 * kBoxBytes, &tmA1l, st * PBK, row, bar);
+            kb = st * PBK;
+          } else {
+            tma_load_2d_pair(dst, &tmA2h, (st - nst1) * PBK, row, bar);
+            tma_load_2d_pair(dst + 2 * kBoxBytes, &tmA2l, (st - nst1) * PBK, row, bar);
+            kb = p.K1 + (st - nst1) * PBK;
+          }
+          tma_load_2d_pair(dst + 4 * kBoxBytes, &tmBh, bcol, kb, bar);
+          tma_load_2d_pair(dst + 5 * kBoxBytes, &tmBh, bcol + 64, kb, bar);
+          tma_load_2d_pair(dst + 6 * kBoxBytes, &tmBl, bcol, kb, bar);
+          tma_load_2d_pair(dst + 7 * kBoxBytes, &tmBl, bcol + 64, kb, bar);
+        }
+      }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      uint32_t it = 0;
+      for (int64_t u = pair; u < nunits; u += npairs)
+        for (int st = 0; st < nst; ++st, ++it) issue_window<true>(base, sm, tmem, it, it);
+    }
+  } else {
+    setmaxnreg_inc<216>();
+    const uint32_t tempty0 = mapa_u32(&sm->tempty[0], 0);
+    const int q = warp & 3, cb = (warp - 4) >> 2;
+    float alpha = p.alpha_host;
+    if (p.mode == 0 && p.scal) alpha = (float)(1.0 / p.scal[GPP_S_VN]);
+    // [A1 | A2] share the accumulator: their planes carry the SAME scale (the caller splits A2 with A1's exponent)
+    const int eA = exp_of_bits(p.amax_a1), eB = exp_of_bits(p.amax_b);
+    const float os = exp2f((float)(eA + eB - 2 * kF16Top));
+    uint32_t w = 0;
+    for (int64_t u = pair; u < nunits; u += npairs) {
+      const int64_t rt = u / p.col_tiles;
+      const int ct = (int)(u - rt * p.col_tiles);
+      float acc[128];
+#pragma unroll
+      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      for (int st = 0; st < nst; ++st, ++w) drain_window(sm, tmem, tempty0, w, acc);
+      const int64_t row = rt * kTileM + rank * 128 + q * 32 + lane;
+      const int col0 = ct * kTileN + cb * 128;
+      float xb2 = 0.f;
+      if (row < p.n) {
+        if (p.mode == 0) {
+          float quad = 0.f;
+          const float* xr = p.X + row * p.ldx + col0;
+          float* orow = p.out + row * p.ldo + col0;
+#pragma unroll
+          for (int i = 0; i < 128; i += 4) {
+            if (col0 + i < p.ncols) {
+              const float4 x = *reinterpret_cast<const float4*>(xr + i);
+              float4 o;
+              o.x = (x.x - os * acc[i + 0]) * alpha;
+              o.y = (x.y - os * acc[i + 1]) * alpha;
+              o.z = (x.z - os * acc[i + 2]) * alpha;
+              o.w = (x.w - os * acc[i + 3]) * alpha;
+              *reinterpret_cast<float4*>(orow + i) = o;
+              quad = fmaf(x.x, o.x, quad); quad = fmaf(x.y, o.y, quad);
+              quad = fmaf(x.z, o.z, quad); quad = fmaf(x.w, o.w, quad);
+              xb2 = fmaf(o.x, o.x, xb2); xb2 = fmaf(o.y, o.y, xb2);
+              xb2 = fmaf(o.z, o.z, xb2); xb2 = fmaf(o.w, o.w, xb2);
+            }
+          }
+          if (p.quad_part) p.quad_part[(int64_t)(ct * 2 + cb) * p.n + row] = quad;
+        } else {
+          float* orow = p.out + row * p.ldo + col0;
+          const float a = alpha * os;
+#pragma unroll
+          for (int i = 0; i < 128; i += 4)
+            if (col0 + i < p.ncols)
+              *reinterpret_cast<float4*>(orow + i) = make_float4(a * acc[i], a * acc[i + 1], a * acc[i + 2], a * acc[i + 3]);
+        }
+      }
+      if (p.mode == 0 && p.xb2_part) {
+        const float s = warp_sum(xb2);
+        if (lane == 0) p.xb2_part[u * 16 + rank * 8 + (warp - 4)] = (double)s;
+      }
+    }
+  }
+  pl_epilogue(tmem);
+}
+
+// =====================================================================================================
+// Producers of planes
+// =====================================================================================================
+// planes buffer (caller-owned, opaque to the caller):
+//   [meta: 64 x u32][colsq: cols doubles][hi: n x ldp halfs][lo: n x ldp halfs],  ldp = cols rounded up to 8
+// meta[0] = bit pattern of max|x| (the exponent of the common scale), meta[1] = 1 when colsq holds the column sums of
+// squares of the source matrix.
+struct PlanesView {
+  uint32_t* meta;
+  double* colsq;
+  __half* hi;
+  __half* lo;
+  int64_t ldp;
+};
+__host__ __device__ inline int64_t planes_ld(int cols) { return ((int64_t)cols + 7) / 8 * 8; }
+inline size_t planes_off_colsq() { return 256; }
+inline size_t planes_off_hi(int cols) { return 256 + align_up((size_t)cols * 8, 256); }
+inline size_t planes_plane_bytes(int64_t n, int cols) { return align_up((size_t)(n > 0 ? n : 1) * planes_ld(cols) * 2, 256); }
+inline PlanesView planes_view(void* buf, int64_t n, int cols) {
+  char* b = static_cast<char*>(buf);
+  PlanesView v;
+  v.meta = reinterpret_cast<uint32_t*>(b);
+  v.colsq = reinterpret_cast<double*>(b + planes_off_colsq());
+  v.hi = reinterpret_cast<__half*>(b + planes_off_hi(cols));
+  v.lo = reinterpret_cast<__half*>(b + planes_off_hi(cols) + planes_plane_bytes(n, cols));
+  v.ldp = planes_ld(cols);
+  return v;
+}
+
+__device__ __forceinline__ void split4(const float4 v, float sc, uint2& h, uint2& l) {
+  const float hx = hi11_round(__float_as_uint(v.x)), hy = hi11_round(__float_as_uint(v.y));
+  const float hz = hi11_round(__float_as_uint(v.z)), hw = hi11_round(__float_as_uint(v.w));
+  h.x = pack_f16x2(hx * sc, hy * sc);
+  h.y = pack_f16x2(hz * sc, hw * sc);
+  l.x = pack_f16x2((v.x - hx) * sc, (v.y - hy) * sc);
+  l.y = pack_f16x2((v.z - hz) * sc, (v.w - hw) * sc);
+}
+
+constexpr int kSplitRowBlocks = 8;   // CTAs per SM's worth of row blocks (grid.y = this x SMs / grid.x)
+
+// fp32 matrix -> planes (+ optional per-row-block column sums of squares, fp64).  Thread = one float4 column group,
+// walking the rows of its block: coalesced 16-byte loads, 8-byte stores into each plane.
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int cols, __half* __restrict__ H,
+                    __half* __restrict__ Lo, int64_t ldp, const uint32_t* __restrict__ amax, int64_t rows_per_block,
+                    double* __restrict__ colsq_part) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const float sc = exp2f((float)(kF16Top - exp_of_bits(amax)));
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(n, r0 + rows_per_block);
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 4
+  for (int64_t r = r0; r < r1; ++r) {
+    const float4 v = *reinterpret_cast<const float4*>(X + r * ldx + c);
+    uint2 h, l;
+    split4(v, sc, h, l);
+    *reinterpret_cast<uint2*>(H + r * ldp + c) = h;
+    *reinterpret_cast<uint2*>(Lo + r * ldp + c) = l;
+    if (colsq_part) {
+      s0 = fma((double)v.x, (double)v.x, s0); s1 = fma((double)v.y, (double)v.y, s1);
+      s2 = fma((double)v.z, (double)v.z, s2); s3 = fma((double)v.w, (double)v.w, s3);
+    }
+  }
+  if (colsq_part) {
+    double* o = colsq_part + (int64_t)blockIdx.y * cols + c;
+    o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
+  }
+}
+
+// Khatri-Rao map (vmod.py:28-35) writing V (fp32, what the API returns) AND its planes AND the exact column sums of
+// squares in one sweep: same thread layout as split_planes_kernel, the thread's four (j, k) pairs are loop-invariant.
+__global__ void __launch_bounds__(256)
+kr_planes_kernel(const float* __restrict__ xn, int64_t P, int p, const float* __restrict__ wn, int64_t nviews, int q,
+                 const int64_t* __restrict__ d, const int64_t* __restrict__ w, int64_t n, float* __restrict__ V,
+                 int64_t ldv, __half* __restrict__ H, __half* __restrict__ Lo, int64_t ldp, int64_t rows_per_block,
+                 double* __restrict__ colsq_part) {
+  const int cols = p * q;
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  int j[4], k[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    j[e] = (c + e) / q;
+    k[e] = (c + e) - j[e] * q;
+  }
+  const bool quad = (q & 3) == 0;   // the four columns share j and their k are one aligned float4 of the view row
+  const float sc = exp2f((float)(kF16Top - 1));   // |v| <= 1 (product of two unit-norm rows): max|v| < 2^1
+  const float qnan = __int_as_float(0x7fc00000);
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(n, r0 + rows_per_block);
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll 4
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t di = d[r], wi = w[r];
+    const bool ok = (di >= 0) & (di < P) & (wi >= 0) & (wi < nviews);
+    float4 v = make_float4(qnan, qnan, qnan, qnan);
+    if (ok) {
+      const float* xr = xn + di * p;
+      const float* wr = wn + wi * q;
+      if (quad) {
+        const float x = xr[j[0]];
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + k[0]);
+        v = make_float4(x * w4.x, x * w4.y, x * w4.z, x * w4.w);
+      } else {
+        v = make_float4(xr[j[0]] * wr[k[0]], xr[j[1]] * wr[k[1]], xr[j[2]] * wr[k[2]], xr[j[3]] * wr[k[3]]);
+      }
+    }
+    *reinterpret_cast<float4*>(V + r * ldv + c) = v;
+    uint2 h, l;
+    split4(v, sc, h, l);
+    *reinterpret_cast<uint2*>(H + r * ldp + c) = h;
+    *reinterpret_cast<uint2*>(Lo + r * ldp + c) = l;
+    s0 = fma((double)v.x, (double)v.x, s0); s1 = fma((double)v.y, (double)v.y, s1);
+    s2 = fma((double)v.z, (double)v.z, s2); s3 = fma((double)v.w, (double)v.w, s3);
+  }
+  double* o = colsq_part + (int64_t)blockIdx.y * cols + c;
+  o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
+}
+
+// colsq[c] = sum over the row blocks, in a fixed order; meta[1] = 1
+__global__ void __launch_bounds__(256) colsq_reduce_kernel(const double* __restrict__ part, int nparts, int cols,
+                                                           double* __restrict__ colsq, uint32_t* __restrict__ meta) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < cols) {
+    double s = 0;
+    for (int i = 0; i < nparts; ++i) s += part[(int64_t)i * cols + c];
+    colsq[c] = s;
+  }
+  if (c == 0) meta[1] = 1u;
+}
+
+__global__ void planes_meta_kernel(uint32_t* meta, uint32_t amax_bits, uint32_t has_colsq) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (amax_bits) meta[0] = amax_bits;
+    meta[1] = has_colsq;
+  }
+}
+__global__ void copy_u32_kernel(uint32_t* dst, const uint32_t* src) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
+}
+
+void split_grid(int64_t n, int cols, dim3& grid, int64_t& rows_per_block) {
+  const int gx = (int)ceil_div(cols, 1024);
+  int64_t gy = (int64_t)kSplitRowBlocks * sm_count() / gx;
+  if (gy < 1) gy = 1;
+  if (gy > ceil_div(n, 16)) gy = ceil_div(n, 16);
+  if (gy < 1) gy = 1;
+  rows_per_block = ceil_div(n > 0 ? n : 1, gy);
+  gy = ceil_div(n > 0 ? n : 1, rows_per_block);
+  grid = dim3((unsigned)gx, (unsigned)gy);
+}
+
+template <typename K>
+int pl_pair_count(K kernel) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (unsigned)sm_count());
+  cfg.blockDim = dim3(kPlThreads);
+  cfg.dynamicSmemBytes = kPlSmemBytes;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = sm_count() / 2;
+  }
+  return n;
+}
+
+constexpr int kMaxDevices = 64;
+std::mutex g_pl_mutex;
+int pl_pairs() {
+  static int n[kMaxDevices] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  std::lock_guard<std::mutex> lock(g_pl_mutex);
+  if (n[dev] == 0) {
+    cudaFuncSetAttribute(pl_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlSmemBytes);
+    cudaFuncSetAttribute(pl_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlSmemBytes);
+    const int a = pl_pair_count(pl_pass1_kernel), b = pl_pair_count(pl_rows_kernel);
+    n[dev] = a < b ? a : b;
+  }
+  return n[dev];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- planes: sizes and producers
+size_t planes_bytes(int64_t n, int cols) { return planes_off_hi(cols) + 2 * planes_plane_bytes(n, cols); }
+
+size_t split_workspace_bytes(int64_t n, int cols) {
+  dim3 grid;
+  int64_t rpb;
+  split_grid(n, cols, grid, rpb);
+  return align_up((size_t)grid.y * cols * sizeof(double), 256);
+}
+
+// X (n x cols fp32) -> planes.  exp_hint != 0: max|x| < 2^exp_hint is known (no scan);  share_scale_of: take the scale
+// from another planes buffer (operands that share an accumulator).  want_colsq needs ws (split_workspace_bytes).
+int launch_split_planes(const float* X, int64_t ldx, int64_t n, int cols, void* planes, const void* share_scale_of,
+                        int exp_hint, bool want_colsq, void* ws, size_t ws_bytes, cudaStream_t st) {
+  PlanesView pv = planes_view(planes, n, cols);
+  if (share_scale_of) {
+    copy_u32_kernel<<<1, 32, 0, st>>>(pv.meta, static_cast<const uint32_t*>(share_scale_of));
+    GPP_LAUNCH_CHECK();
+  } else if (exp_hint != 0) {
+    // bit pattern of 2^(exp_hint - 1): exponent field exp_hint - 1 + 127
+    planes_meta_kernel<<<1, 32, 0, st>>>(pv.meta, (uint32_t)(exp_hint - 1 + 127) << 23, 0u);
+    GPP_LAUNCH_CHECK();
+  } else {
+    GPP_TRY(tc_absmax(X, ldx, n, cols, pv.meta, st));
+  }
+  if (n <= 0) return GPP_OK;
+  dim3 grid;
+  int64_t rpb;
+  split_grid(n, cols, grid, rpb);
+  double* part = nullptr;
+  if (want_colsq) {
+    const size_t need = align_up((size_t)grid.y * cols * sizeof(double), 256);
+    if (!ws || ws_bytes < need) {
+      set_error("split_planes: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+      return GPP_ERR_WORKSPACE;
+    }
+    part = static_cast<double*>(ws);
+  }
+  split_planes_kernel<<<grid, 256, 0, st>>>(X, ldx, n, cols, pv.hi, pv.lo, pv.ldp, pv.meta, rpb, part);
+  GPP_LAUNCH_CHECK();
+  if (want_colsq) {
+    colsq_reduce_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, st>>>(part, (int)grid.y, cols, pv.colsq, pv.meta);
+    GPP_LAUNCH_CHECK();
+  } else {
+    planes_meta_kernel<<<1, 32, 0, st>>>(pv.meta, 0u, 0u);
+    GPP_LAUNCH_CHECK();
+  }
+  return GPP_OK;
+}
+
+int launch_kr_planes(const float* xn, int64_t P, int p, const float* wn, int64_t nviews, int q, const int64_t* d,
+                     const int64_t* w, int64_t n, float* V, int64_t ldv, void* planes, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  const int cols = p * q;
+  PlanesView pv = planes_view(planes, n, cols);
+  planes_meta_kernel<<<1, 32, 0, st>>>(pv.meta, (uint32_t)(1 - 1 + 127) << 23, 0u);   // max|v| < 2^1
+  GPP_LAUNCH_CHECK();
+  if (n <= 0) return GPP_OK;
+  dim3 grid;
+  int64_t rpb;
+  split_grid(n, cols, grid, rpb);
+  const size_t need = align_up((size_t)grid.y * cols * sizeof(double), 256);
+  if (!ws || ws_bytes < need) {
+    set_error("khatri_rao_fwd_planes: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return GPP_ERR_WORKSPACE;
+  }
+  double* part = static_cast<double*>(ws);
+  kr_planes_kernel<<<grid, 256, 0, st>>>(xn, P, p, wn, nviews, q, d, w, n, V, ldv, pv.hi, pv.lo, pv.ldp, rpb, part);
+  GPP_LAUNCH_CHECK();
+  colsq_reduce_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, st>>>(part, (int)grid.y, cols, pv.colsq, pv.meta);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
+// ---------------------------------------------------------------- pass 1 on planes
+bool pl_pass1_supported(int64_t n, int Q, int L) { return Q >= 128 && n >= 512 && tc_available(); }
+
+size_t pl_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g) {
+  Pass1Params p{};
+  pass1_geometry(n, Q, L, skip_g, pl_pairs(), PBK, p);
+  return (size_t)p.tiles * p.splits * kTileM * kTileN * sizeof(float) + 256 /* wave counter */;
+}
+
+// G (Q x Q, optional) = V^T V and C (Q x L) = V^T X from planes.  use_colsq: overwrite the diagonal of G with the exact
+// column sums of squares stored with V's planes (they must have been produced with want_colsq).
+int launch_pl_pass1(const void* planesV, const void* planesX, int64_t n, int Q, int L, float* G, int64_t ldg, float* C,
+                    int64_t ldc, bool use_colsq, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Pass1Params p{};
+  pass1_geometry(n, Q, L, G == nullptr, pl_pairs(), PBK, p);
+  const size_t part_bytes = (size_t)p.tiles * p.splits * kTileM * kTileN * sizeof(float), need = part_bytes + 256;
+  if (!ws || ws_bytes < need) {
+    set_error("gram_vtz (planes): workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return GPP_ERR_WORKSPACE;
+  }
+  if (p.tiles == 0) return GPP_OK;
+  const PlanesView pv = planes_view(const_cast<void*>(planesV), n, Q);
+  const PlanesView px = L > 0 ? planes_view(const_cast<void*>(planesX), n, L) : pv;
+  p.partial = static_cast<float*>(ws);
+  p.amax = pv.meta;
+  p.amax_x = px.meta;
+  p.wave_ctr = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + part_bytes);
+  if (const char* e = getenv("GPP_TC_WAVE_SYNC")) {   // experiment knob: 0 switches the wave alignment off
+    if (e[0] == '0') p.wave_ctr = nullptr;
+  }
+  if (p.wave_ctr) GPP_CUDA(cudaMemsetAsync(p.wave_ctr, 0, 4, st));
+  p.G = G; p.ldg = ldg; p.C = C; p.ldc = ldc; p.scal_c = nullptr;
+  p.diag = (use_colsq && G) ? pv.colsq : nullptr;
+  CUtensorMap tmVh, tmVl, tmXh, tmXl;
+  GPP_TRY(make_tensor_map_2d(&tmVh, pv.hi, 2, n, Q, pv.ldp, 64, PBK, CU_TENSOR_MAP_SWIZZLE_128B));
+  GPP_TRY(make_tensor_map_2d(&tmVl, pv.lo, 2, n, Q, pv.ldp, 64, PBK, CU_TENSOR_MAP_SWIZZLE_128B));
+  if (L > 0) {
+    GPP_TRY(make_tensor_map_2d(&tmXh, px.hi, 2, n, L, px.ldp, 64, PBK, CU_TENSOR_MAP_SWIZZLE_128B));
+    GPP_TRY(make_tensor_map_2d(&tmXl, px.lo, 2, n, L, px.ldp, 64, PBK, CU_TENSOR_MAP_SWIZZLE_128B));
+  } else {
+    tmXh = tmVh;
+    tmXl = tmVl;
+  }
+  const int nunits = p.tiles * p.splits;
+  const int pairs = nunits < pl_pairs() ? nunits : pl_pairs();
+  pl_pass1_kernel<<<2 * pairs, kPlThreads, kPlSmemBytes, st>>>(tmVh, tmVl, tmXh, tmXl, p);
+  GPP_LAUNCH_CHECK();
+  return launch_pass1_reduce(p, st);
+}
+
+// ---------------------------------------------------------------- row GEMMs on planes
+bool pl_rows_supported(int64_t n, int K, int ncols) { return n >= 512 && K >= 64 && ncols >= 64 && tc_available(); }
+
+static int launch_pl_rows(const PlanesView& a1, int K1, const PlanesView* a2, int K2, const PlanesView& b, int64_t n,
+                          int ncols, PlRowsParams& p, cudaStream_t st) {
+  p.n = n; p.K1 = K1; p.K2 = K2; p.ncols = ncols;
+  p.col_tiles = (int)ceil_div(ncols, kTileN);
+  p.row_tiles = ceil_div(n, kTileM);
+  p.amax_a1 = a1.meta; p.amax_a2 = a2 ? a2->meta : a1.meta; p.amax_b = b.meta;
+  CUtensorMap tA1h, tA1l, tA2h, tA2l, tBh, tBl;
+  GPP_TRY(make_tensor_map_2d(&tA1h, a1.hi, 2, n, K1, a1.ldp, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+  GPP_TRY(make_tensor_map_2d(&tA1l, a1.lo, 2, n, K1, a1.ldp, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+  if (a2 && K2 > 0) {
+    GPP_TRY(make_tensor_map_2d(&tA2h, a2->hi, 2, n, K2, a2->ldp, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+    GPP_TRY(make_tensor_map_2d(&tA2l, a2->lo, 2, n, K2, a2->ldp, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B));
+  } else {
+    tA2h = tA1h;
+    tA2l = tA1l;
+  }
+  GPP_TRY(make_tensor_map_2d(&tBh, b.hi, 2, (int64_t)K1 + K2, ncols, b.ldp, 64, PBK, CU_TENSOR_MAP_SWIZZLE_128B));
+  GPP_TRY(make_tensor_map_2d(&tBl, b.lo, 2, (int64_t)K1 + K2, ncols, b.ldp, 64, PBK, CU_TENSOR_MAP_SWIZZLE_128B));
+  const int64_t nunits = p.row_tiles * p.col_tiles;
+  const int pairs = (int)(nunits < pl_pairs() ? nunits : pl_pairs());
+  if (pairs <= 0) return GPP_OK;
+  pl_rows_kernel<<<2 * pairs, kPlThreads, kPlSmemBytes, st>>>(tA1h, tA1l, tA2h, tA2l, tBh, tBl, p);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
+// workspace of pass 2: planes of W, the quad / xb2 partials and the finalize scratch
+size_t pl_xb_workspace_bytes(int64_t n, int Q, int L) {
+  const int64_t col_tiles = ceil_div(L, kTileN), row_tiles = ceil_div(n, kTileM);
+  return align_up(planes_bytes(Q, L), 256) + align_up((size_t)col_tiles * 2 * n * sizeof(float), 256) +
+         align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256) + align_up(xb_finalize_bytes(), 256);
+}
+
+// Xb = alpha (X - V W) from the planes of V (W is split here: Q x L, small); with nll != nullptr the NLL epilogue.
+int launch_pl_xb(const void* planesV, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n, int Q, int L,
+                 double* scal, float alpha_host, float* Xb, int64_t ldxb, float* nll, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+  const size_t need = pl_xb_workspace_bytes(n, Q, L);
+  if (!ws || ws_bytes < need) {
+    set_error("xb_nll (planes): workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return GPP_ERR_WORKSPACE;
+  }
+  char* wsb = static_cast<char*>(ws);
+  void* planesW = wsb;
+  size_t off = align_up(planes_bytes(Q, L), 256);
+  GPP_TRY(launch_split_planes(W, ldw, Q, L, planesW, nullptr, 0, false, nullptr, 0, st));
+  const int64_t col_tiles = ceil_div(L, kTileN), row_tiles = ceil_div(n, kTileM);
+  PlRowsParams p{};
+  p.mode = 0; p.X = X; p.ldx = ldx; p.out = Xb; p.ldo = ldxb; p.scal = scal; p.alpha_host = alpha_host;
+  if (nll) {
+    p.quad_part = reinterpret_cast<float*>(wsb + off);
+    off += align_up((size_t)col_tiles * 2 * n * sizeof(float), 256);
+    p.xb2_part = reinterpret_cast<double*>(wsb + off);
+    off += align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256);
+  }
+  const PlanesView pv = planes_view(const_cast<void*>(planesV), n, Q);
+  const PlanesView pw = planes_view(planesW, Q, L);
+  GPP_TRY(launch_pl_rows(pv, Q, nullptr, 0, pw, n, L, p, st));
+  if (nll) {
+    double* fin = reinterpret_cast<double*>(wsb + off);
+    GPP_TRY(launch_xb_finalize(p.quad_part, (int)(col_tiles * 2), n, p.xb2_part, row_tiles * col_tiles * 16, fin, scal,
+                               nll, st));
+  }
+  return GPP_OK;
+}
+
+}  // namespace gpp

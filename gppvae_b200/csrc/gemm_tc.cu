@@ -50,8 +50,11 @@
 // tile, tc_reduce_kernel sums them in a fixed order (fp64) and tc_mirror_kernel fills the upper triangle of G.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "pass1_common.cuh"
 #include "tc_common.cuh"
 
 namespace gpp {
@@ -66,7 +69,7 @@ namespace {
 #ifndef GPP_TC_LO
 #define GPP_TC_LO 8      // converted slots in flight (fp16 planes of B in shared memory + A slot in TMEM): converter -> MMA
 #endif
-constexpr int TM = 256, TN = 256;   // tile of a CTA pair
+constexpr int TM = kTileM, TN = kTileN;   // tile of a CTA pair
 constexpr int HM = 128, HN = 128;   // what one CTA stages of it
 constexpr int TBK = 16, kRaw = GPP_TC_RAW, kLo = GPP_TC_LO;
 #ifndef GPP_TC_GROUP
@@ -99,13 +102,6 @@ constexpr int kSmemBytes = kRaw * kRawBytes + kLo * kBBytes + 1024 /*align*/ + 5
 struct F16Scales {
   float a32, a_hi, a_lo, b_hi, b_lo, out;
 };
-__device__ __forceinline__ int exp_of_bits(const uint32_t* p) {
-  if (!p) return 0;
-  const uint32_t b = *p;
-  if (b == 0) return 0;
-  const int e = (int)((b >> 23) & 0xFF) - 126;   // 2^(e-1) <= max|x| < 2^e
-  return e < -50 ? -50 : (e > 50 ? 50 : e);
-}
 // The 11 leading significant bits of an fp32 number (given as its bit pattern): the tf32 pipe truncates, so its split
 // truncates too; the fp16 split rounds (half away from zero), which halves the remainder and makes its sign random --
 // the dropped lo.lo term is then zero-mean instead of a coherent bias.
@@ -113,27 +109,7 @@ template <bool F16>
 __device__ __forceinline__ float hi11(uint32_t bits) {
   return __uint_as_float(F16 ? ((bits + 0x1000u) & 0xFFFFE000u) : (bits & 0xFFFFE000u));
 }
-// fp16 split: hi = the operand rounded to 11 significant bits (exactly an fp16 number), lo = the remainder rounded to
-// fp16, BOTH scaled by the same power of two per operand, 2^(kF16Top - e) with max|x| < 2^e, so that hi.hi, hi.lo and
-// lo.hi share one scale and one accumulator.  kF16Top = 7 puts the largest magnitude below 128: 2^8 of headroom to the
-// fp16 maximum for rows the magnitude sample did not see, and a remainder that stays a normal fp16 number for every
-// element above 2^-10 of the maximum (below that the error is bounded by 2^-32 of the maximum).
-constexpr int kF16Top = 7;
-// The tensor core adds into its fp32 accumulator with truncation.  On coherent (same-sign) sums that is a relative bias
-// of -1.4e-7 ... -3.1e-7 for this window schedule, depending on the spread of the magnitudes (experiments/bench/
-// bias_cal.py; the tf32 split measures -0.4e-7 ... -2.8e-7, part of it hidden by its over-counted lo.lo term); on
-// mixed-sign sums it is smaller (the NLL experiment below is consistent with about half).  A common relative bias of G and V^T Z cancels in W = r B^-1 C; what does
-// not cancel is the DIFFERENCE between the entries that are same-sign by construction -- the diagonal of the Gram
-// matrix, G_ii = sum v^2 -- and the rest: a diagonal that is 1e-7 smaller than its surroundings makes B too small and W
-// too large, which the NLL sees amplified (experiments/bench/smoke_diag.py, six shapes: NLL error -0.9e-6 ... -6e-6
-// without a correction, +1.3e-6 ... +6.5e-6 with the full coherent bias 2.2e-7 added back to the diagonal, zero at
-// 0.9e-7 ... 1.2e-7 in all six).  The fp16 split therefore scales the diagonal entries of G by 1 + kDiagComp in the
-// fp64 reduction of pass 1.  (Scaling every finished sum in the drain instead -- which centres all-positive test
-// matrices -- over-corrects the mixed-sign products of pass 2: NLL error -3.9e-6 per 1e-7 of compensation.)
-#ifndef GPP_TC_DIAGCOMP
-#define GPP_TC_DIAGCOMP 1.1e-7
-#endif
-constexpr double kDiagComp = GPP_TC_DIAGCOMP;
+// (the fp16 split and its common scale kF16Top are described in pass1_common.cuh)
 // tf32 split: each fp16 factor of the correction terms is normalised by its own operand's magnitude,
 //   a.lo(b) -> (a 2^-eA) . (lo(b) 2^(11 - eB))      lo(a).b -> (lo(a) 2^(11 - eA)) . (b 2^-eB)
 // both scaled by 2^g, g = 11 - eA - eB; hi.hi is brought to the same scale by writing a 2^g (exact) as its A operand.
@@ -192,44 +168,6 @@ struct TcShared {
   uint64_t full[kRaw], empty[kRaw], conv[kLo], lo_empty[kLo], tfull[2], tempty[2];
   uint32_t tmem_base;
 };
-
-struct Pass1Params {
-  int64_t n;
-  int Q, L;
-  int tm_count;      // ceil(Q / 256)
-  int tiles_g;       // lower-triangular tiles of G: (tm, tn) with tn <= tm
-  int tn_c;          // ceil(L / 256)
-  int tiles;         // tiles_g + tm_count * tn_c
-  int splits;
-  int64_t rows_per_split;  // multiple of TBK
-  float* partial;          // [tile][split][TM * TN]
-  float* G; int64_t ldg;   // V^T V  (not touched when tiles_g == 0)
-  float* C; int64_t ldc;   // V^T X
-  const double* scal_c;    // when set: C *= scal[V0] / scal[VN]
-  double diag_scale;       // factor applied to the diagonal entries of G in the reduction (1 + kDiagComp, or 1)
-  const uint32_t* amax;    // device: [0] bits of max|V|, [1] bits of max|X| (fp16 scales); may be null
-  unsigned int* wave_ctr;  // device, zeroed before the launch: producer-units issued so far (wave alignment); may be null
-};
-
-__device__ __forceinline__ void decode_tile(const Pass1Params& p, int tile, int& tm, int& tn, bool& is_c) {
-  if (tile < p.tiles_g) {
-    is_c = false;
-    int t = 0;
-    while ((t + 1) * (t + 2) / 2 <= tile) ++t;
-    tm = t;
-    tn = tile - t * (t + 1) / 2;
-  } else {
-    is_c = true;
-    const int r = tile - p.tiles_g;
-    tm = r / p.tn_c;
-    tn = r - tm * p.tn_c;
-  }
-}
-
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- pieces shared by the two kernels ----------------------------------------------------------------------
 // Raw slots are handed back to the TMA producer by the MMA commit in both splits.  (Releasing them from the converter
@@ -633,12 +571,12 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(Pass1Params p) {
       const float4 v = *reinterpret_cast<const float4*>(src + (size_t)s * (TM * TN) + r * TN + c4);
       s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
     }
-    if (!is_c && tm == tn) {   // diagonal entries of G: same-sign sums, see kDiagComp
+    if (!is_c && tm == tn && p.diag) {   // diagonal entries of G: the exactly accumulated column sums of squares
       const int dc = row0 + r - (col0 + c4);
-      if (dc == 0) s0 *= p.diag_scale;
-      else if (dc == 1) s1 *= p.diag_scale;
-      else if (dc == 2) s2 *= p.diag_scale;
-      else if (dc == 3) s3 *= p.diag_scale;
+      if (dc == 0) s0 = p.diag[row0 + r];
+      else if (dc == 1) s1 = p.diag[row0 + r];
+      else if (dc == 2) s2 = p.diag[row0 + r];
+      else if (dc == 3) s3 = p.diag[row0 + r];
     }
     float* dst = (is_c ? p.C + (int64_t)(row0 + r) * p.ldc : p.G + (int64_t)(row0 + r) * p.ldg) + col0 + c4;
     *reinterpret_cast<float4*>(dst) =
@@ -904,41 +842,43 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D fp32 row-major matrix (rows x cols, leading dimension ld), box = {box_cols floats, box_rows rows}.
-int make_map_2d(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
-                CUtensorMapSwizzle swz) {
+// 2-D row-major matrix (rows x cols, leading dimension ld elements), box = {box_cols elements, box_rows rows}.
+int make_map_2d_any(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                    int box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return GPP_ERR_CUDA;
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, (long long)rows,
-              (long long)cols, (long long)ld);
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld elem=%d)", (int)r,
+              (long long)rows, (long long)cols, (long long)ld, elem_bytes);
     return GPP_ERR_CUDA;
   }
   return GPP_OK;
 }
+int make_map_2d(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                CUtensorMapSwizzle swz) {
+  return make_map_2d_any(m, ptr, 4, rows, cols, ld, box_cols, box_rows, swz);
+}
 
-// Record the bit pattern of max|X| over (a sample of) X in *slot (zeroed here); the kernels derive the power-of-two
-// scales of the fp16 operands from it.  Large row operands are sampled: about 8192 rows at a constant stride over the
-// whole matrix (not its head -- rows are often sorted by object).  The fp16 split leaves 2^8 of headroom above the
-// sampled maximum before an element saturates (kF16Top), the tf32 split 2^16.
-constexpr int64_t kAbsmaxSampleRows = 8192;
+// Record the bit pattern of max|X| over ALL of X in *slot (zeroed here); the kernels derive the power-of-two scales of
+// the fp16 operands from it.  The scan is exact (one streaming read, cheap next to the GEMM it feeds): an operand scaled
+// from a sampled maximum would silently saturate on an outlier row the sample missed.
 int launch_absmax(const float* X, int64_t ld, int64_t rows, int cols, uint32_t* slot, cudaStream_t st) {
   GPP_CUDA(cudaMemsetAsync(slot, 0, 4, st));
   if (rows <= 0 || cols < 4) return GPP_OK;
-  const int64_t stride = rows > kAbsmaxSampleRows ? rows / kAbsmaxSampleRows : 1;
-  const int64_t sampled = (rows + stride - 1) / stride;
-  const int grid = (int)(sampled < 592 ? sampled : 592);
-  absmax_bits_kernel<<<grid, 256, 0, st>>>(X, ld * stride, sampled, cols, slot);
+  const int64_t want = ceil_div(rows * (int64_t)cols, 256 * 4 * 8);   // ~8 float4 per thread
+  const int cap = 8 * sm_count();
+  const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+  absmax_bits_kernel<<<grid, 256, 0, st>>>(X, ld, rows, cols, slot);
   GPP_LAUNCH_CHECK();
   return GPP_OK;
 }
@@ -962,26 +902,40 @@ int pair_count(K kernel) {
   return n;
 }
 
+// per-device caches (a second device in the process needs its own cudaFuncSetAttribute and occupancy query)
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+std::mutex g_attr_mutex;
 int pass1_pairs() {
-  static int n = 0;
-  if (n == 0) {
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  if (n[dev] == 0) {
     cudaFuncSetAttribute(tc_pass1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(tc_pass1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    n = pair_count(tc_pass1_kernel<true>);
+    n[dev] = pair_count(tc_pass1_kernel<true>);
   }
-  return n;
+  return n[dev];
 }
 int rows_pairs() {
-  static int n = 0;
-  if (n == 0) {
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  if (n[dev] == 0) {
     cudaFuncSetAttribute(tc_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     cudaFuncSetAttribute(tc_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    n = pair_count(tc_rows_kernel<true>);
+    n[dev] = pair_count(tc_rows_kernel<true>);
   }
-  return n;
+  return n[dev];
 }
 
-void pass1_geometry(int64_t n, int Q, int L, bool skip_g, Pass1Params& p) {
+}  // namespace
+
+void pass1_geometry(int64_t n, int Q, int L, bool skip_g, int pairs, int kblock, Pass1Params& p) {
   p.n = n; p.Q = Q; p.L = L;
   p.tm_count = (int)ceil_div(Q, TM);
   p.tiles_g = skip_g ? 0 : p.tm_count * (p.tm_count + 1) / 2;
@@ -989,9 +943,8 @@ void pass1_geometry(int64_t n, int Q, int L, bool skip_g, Pass1Params& p) {
   p.tiles = p.tiles_g + p.tm_count * p.tn_c;
   // choose the split count: best wave efficiency on the persistent grid of CTA pairs, >= 512 rows per split,
   // <= 1 GB of partial tiles
-  const int pairs = pass1_pairs();
   const int64_t max_by_rows = n / 512 > 1 ? n / 512 : 1;
-  const int64_t max_by_ws = (int64_t)(1024ll << 20) / ((int64_t)p.tiles * TM * TN * 4);
+  const int64_t max_by_ws = (int64_t)(1024ll << 20) / ((int64_t)(p.tiles > 0 ? p.tiles : 1) * TM * TN * 4);
   int64_t smax = max_by_rows < max_by_ws ? max_by_rows : max_by_ws;
   if (smax < 1) smax = 1;
   if (smax > 2 * pairs) smax = 2 * pairs;
@@ -1009,11 +962,28 @@ void pass1_geometry(int64_t n, int Q, int L, bool skip_g, Pass1Params& p) {
     const long long r = atoll(e);
     if (r >= 512) best = (int)ceil_div(n > 0 ? n : 1, r);
   }
-  p.rows_per_split = ceil_div(ceil_div(n > 0 ? n : 1, best), TBK) * TBK;
+  p.rows_per_split = ceil_div(ceil_div(n > 0 ? n : 1, best), kblock) * kblock;
   p.splits = (int)ceil_div(n > 0 ? n : 1, p.rows_per_split);
 }
 
-}  // namespace
+int launch_pass1_reduce(const Pass1Params& p, cudaStream_t st) {
+  if (p.tiles == 0) return GPP_OK;
+  tc_reduce_kernel<<<p.tiles * 8, 256, 0, st>>>(p);
+  GPP_LAUNCH_CHECK();
+  if (p.tiles_g > 0 && p.G) {
+    dim3 mg((unsigned)ceil_div(p.Q, 32), (unsigned)ceil_div(p.Q, 32));
+    tc_mirror_kernel<<<mg, 256, 0, st>>>(p.G, p.ldg, p.Q);
+    GPP_LAUNCH_CHECK();
+  }
+  return GPP_OK;
+}
+
+int make_tensor_map_2d(CUtensorMap* m, const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld_elems,
+                       int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+  return make_map_2d_any(m, ptr, elem_bytes, rows, cols, ld_elems, box_cols, box_rows, swz);
+}
+
+bool tc_available() { return encode_fn() != nullptr; }
 
 #ifdef GPP_TC_PROF
 extern "C" int gpp_debug_prof(unsigned long long* out /* [512][16] */) {
@@ -1029,7 +999,7 @@ bool tc_pass1_supported(int64_t n, int Q, int L) { return Q >= 128 && n >= 512 &
 
 size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g) {
   Pass1Params p;
-  pass1_geometry(n, Q, L, skip_g, p);
+  pass1_geometry(n, Q, L, skip_g, pass1_pairs(), TBK, p);
   return (size_t)p.tiles * p.splits * TM * TN * sizeof(float) + 256 /* absmax slots */;
 }
 
@@ -1037,8 +1007,8 @@ size_t tc_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g) {
 int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, int64_t n, int Q, int L, float* G,
                     int64_t ldg, float* C, int64_t ldc, const double* scal_c, void* ws, size_t ws_bytes,
                     bool wide_range, cudaStream_t st) {
-  Pass1Params p;
-  pass1_geometry(n, Q, L, G == nullptr, p);
+  Pass1Params p{};
+  pass1_geometry(n, Q, L, G == nullptr, pass1_pairs(), TBK, p);
   const size_t part_bytes = (size_t)p.tiles * p.splits * TM * TN * sizeof(float), need = part_bytes + 256;
   if (!ws || ws_bytes < need) {
     set_error("gram_vtz (tcgen05): workspace too small (%zu < %zu bytes)", ws_bytes, need);
@@ -1056,7 +1026,6 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
   }
   if (p.wave_ctr) GPP_CUDA(cudaMemsetAsync(p.wave_ctr, 0, 4, st));
   p.G = G; p.ldg = ldg; p.C = C; p.ldc = ldc; p.scal_c = scal_c;
-  p.diag_scale = wide_range ? 1.0 : 1.0 + kDiagComp;
   CUtensorMap tmV, tmX;
   GPP_TRY(make_map_2d(&tmV, V, n, Q, ldv, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   if (L > 0) GPP_TRY(make_map_2d(&tmX, X, n, L, ldx, 32, TBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
@@ -1066,14 +1035,7 @@ int launch_tc_pass1(const float* V, int64_t ldv, const float* X, int64_t ldx, in
   if (wide_range) tc_pass1_kernel<false><<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmV, tmX, p);
   else tc_pass1_kernel<true><<<2 * pairs, kTcThreads, kSmemBytes, st>>>(tmV, tmX, p);
   GPP_LAUNCH_CHECK();
-  tc_reduce_kernel<<<p.tiles * 8, 256, 0, st>>>(p);
-  GPP_LAUNCH_CHECK();
-  if (G) {
-    dim3 mg((unsigned)ceil_div(Q, 32), (unsigned)ceil_div(Q, 32));
-    tc_mirror_kernel<<<mg, 256, 0, st>>>(G, ldg, Q);
-    GPP_LAUNCH_CHECK();
-  }
-  return GPP_OK;
+  return launch_pass1_reduce(p, st);
 }
 
 bool tc_rows_supported(int64_t n, int K, int ncols) { return n >= 512 && K >= 64 && ncols >= 64 && encode_fn() != nullptr; }

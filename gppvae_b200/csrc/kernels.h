@@ -60,6 +60,26 @@ int launch_tc_syrk_sub(float* C, int64_t ldc, const float* A, int64_t lda, const
                        const uint32_t* amax, cudaStream_t st);
 int tc_absmax(const float* X, int64_t ld, int64_t rows, int cols, uint32_t* slot, cudaStream_t st);
 
+bool tc_available();   // cuTensorMapEncodeTiled resolvable from this driver
+
+// ---- gemm_planes.cu (pre-split fp16 operand planes: TMA -> shared memory -> tcgen05, no conversion in the kernel) ----
+size_t planes_bytes(int64_t n, int cols);
+size_t split_workspace_bytes(int64_t n, int cols);
+int launch_split_planes(const float* X, int64_t ldx, int64_t n, int cols, void* planes, const void* share_scale_of,
+                        int exp_hint, bool want_colsq, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_kr_planes(const float* xn, int64_t P, int p, const float* wn, int64_t nviews, int q, const int64_t* d,
+                     const int64_t* w, int64_t n, float* V, int64_t ldv, void* planes, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+bool pl_pass1_supported(int64_t n, int Q, int L);
+size_t pl_pass1_workspace_bytes(int64_t n, int Q, int L, bool skip_g);
+int launch_pl_pass1(const void* planesV, const void* planesX, int64_t n, int Q, int L, float* G, int64_t ldg, float* C,
+                    int64_t ldc, bool use_colsq, void* ws, size_t ws_bytes, cudaStream_t st);
+bool pl_rows_supported(int64_t n, int K, int ncols);
+size_t pl_xb_workspace_bytes(int64_t n, int Q, int L);
+int launch_pl_xb(const void* planesV, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n, int Q, int L,
+                 double* scal, float alpha_host, float* Xb, int64_t ldxb, float* nll, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
+
 bool tc_rows_supported(int64_t n, int K, int ncols);
 size_t tc_xb_workspace_bytes(int64_t n, int L);
 int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n,

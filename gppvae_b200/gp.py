@@ -137,13 +137,20 @@ class _FactorCache:
         self.ldg = 0
         self.fac: Optional[ops.Factorisation] = None
 
-    def lookup(self, key, want_binv: bool):
+    def lookup(self, key, want_binv: bool, vs: torch.Tensor):
         if self.key is not None and self.key == key and (self.fac.Binv is not None or not want_binv):
-            return self.fac
+            # version counters do not see writes through `.data` (the reference itself initialises parameters that way,
+            # vmod.py:37-40): a hit also needs the variances the factorisation was built with, value for value
+            if torch.equal(self.vs_snapshot, vs.detach().to(torch.float32)):
+                return self.fac
         return None
 
-    def store(self, key, keep, G, ldg, fac):
+    def store(self, key, keep, G, ldg, fac, vs: torch.Tensor):
         self.key, self.keep, self.G, self.ldg, self.fac = key, keep, G, ldg, fac
+        self.vs_snapshot = vs.detach().to(torch.float32).clone()
+
+    def clear(self):
+        self.key = self.keep = self.G = self.fac = None
 
 
 class GP(nn.Module):
@@ -161,19 +168,29 @@ class GP(nn.Module):
         self._group = process_group
         self._sharded = process_group is not None
         self._cache = _FactorCache()
-        self._ntotal_cache = {}
+        self._n_total_given = None
         self._vs_ref = None          # weakref to the tensor last returned by get_vs()
         self._vs_version = -1
         self.cache_hits = 0
         self.stage_hook = None       # optional callable(name): bench.py records CUDA events at stage boundaries
 
     # ------------------------------------------------------------------ sharding
-    def shard_rows(self, process_group=None) -> "GP":
-        """Treat the rows handed to every method as this rank's shard of the N rows."""
+    def shard_rows(self, process_group=None, n_total: Optional[int] = None) -> "GP":
+        """Treat the rows handed to every method as this rank's shard of the N rows.
+
+        `n_total` is the global number of rows.  Pass it when it is known (it usually is: the size of the data set):
+        otherwise every evaluation all-reduces its local row count first, which costs a host synchronisation."""
         import torch.distributed as dist
         self._group = process_group if process_group is not None else dist.group.WORLD
         self._sharded = True
+        self._n_total_given = n_total
         return self
+
+    def invalidate_cache(self) -> None:
+        """Forget the cached factorisation and operand planes.  Needed only after writes the version counters cannot
+        see (`V.data[...] = ...`); in-place tensor operations and optimiser steps are detected."""
+        self._cache.clear()
+        ops.PLANES.invalidate()
 
     def _all_reduce(self, t: torch.Tensor) -> None:
         if self._sharded:
@@ -183,11 +200,13 @@ class GP(nn.Module):
     def _n_total(self, n: int, device) -> int:
         if not self._sharded:
             return n
-        if n not in self._ntotal_cache:     # one host sync per distinct shard size, then cached
-            t = torch.tensor([n], device=device, dtype=torch.int64)
-            self._all_reduce(t)
-            self._ntotal_cache[n] = int(t.item())
-        return self._ntotal_cache[n]
+        if self._n_total_given is not None:
+            return int(self._n_total_given)
+        # every rank takes part in this collective on every call (a per-rank cache keyed on the local row count would
+        # let ranks disagree about whether to communicate)
+        t = torch.tensor([n], device=device, dtype=torch.int64)
+        self._all_reduce(t)
+        return int(t.item())
 
     def _stage(self, name: str) -> None:
         if self.stage_hook is not None:
@@ -218,27 +237,31 @@ class GP(nn.Module):
 
     def _factorise(self, Vm, ldv, Q, vs, want_binv: bool, Xm=None, ldx=0, Lk=0, vs_origin=None):
         """Pass 1 (+ all-reduce) and the factorisation, through the cache.
-        Returns (fac, C) with C = V^T X (Q x Lk, summed over ranks) or None when no X was given."""
+        Returns (fac, C, pV) with C = V^T X (Q x Lk, summed over ranks) or None when no X was given, and pV the operand
+        planes of V (None for shapes below the tensor-core tile, which run on the fp32 engine)."""
         n = Vm.shape[0]
         tok, keep_vs = self._vs_token(vs if vs_origin is None else vs_origin)
         key = (Vm.untyped_storage().data_ptr(), Vm.storage_offset(), Vm._version, n, Q, ldv, tok)
-        fac = self._cache.lookup(key, want_binv)
+        use_planes = ops.planes_supported(n, Q, Lk)
+        pV = ops.planes_of(Vm, ldv) if use_planes else None
+        pX = ops.split_planes(Xm, ldx, n, Lk) if (use_planes and Lk) else None
+        fac = self._cache.lookup(key, want_binv, vs)
         if fac is not None:
             self.cache_hits += 1
             C = None
             if Lk:
-                C = ops.atb(Vm, ldv, Xm, ldx, n, Q, Lk)
+                C = ops.atb_planes(pV, pX, n, Q, Lk) if use_planes else ops.atb(Vm, ldv, Xm, ldx, n, Q, Lk)
                 self._all_reduce(C)
-            return fac, C
+            return fac, C, pV
         self._stage("pass1:start")
-        GC = ops.gram_vtz(Vm, ldv, Xm, ldx, n, Q, Lk)
+        GC = ops.gram_vtz_planes(pV, pX, n, Q, Lk) if use_planes else ops.gram_vtz(Vm, ldv, Xm, ldx, n, Q, Lk)
         self._stage("pass1:end")
         self._all_reduce(GC)
         self._stage("allreduce:end")
         fac = ops.factor(GC, Q + Lk, Q, vs, want_binv)
         self._stage("factor:end")
-        self._cache.store(key, (Vm, keep_vs), GC, Q + Lk, fac)
-        return fac, (GC[:, Q:] if Lk else None)
+        self._cache.store(key, (Vm, keep_vs), GC, Q + Lk, fac, vs)
+        return fac, (GC[:, Q:] if Lk else None), pV
 
     # ------------------------------------------------------------------ structured route (vmod.KhatriRao)
     def _kr_c(self, kr: KhatriRao, Xm, ldx, Lk) -> torch.Tensor:
@@ -254,7 +277,7 @@ class GP(nn.Module):
         tok, keep_vs = self._vs_token(vs if vs_origin is None else vs_origin)
         key = ("kr", id(kr), tok)
         Q = kr.p * kr.q
-        fac = self._cache.lookup(key, want_binv)
+        fac = self._cache.lookup(key, want_binv, vs)
         if fac is not None:
             self.cache_hits += 1
             return fac, (self._kr_c(kr, Xm, ldx, Lk) if Lk else None)
@@ -273,7 +296,7 @@ class GP(nn.Module):
         GC = ops.kr_assemble_gc(ST, kr.wn, kr.p, Lx, True)
         fac = ops.factor(GC, Q + Lx, Q, vs, want_binv)
         self._stage("factor:end")
-        self._cache.store(key, (kr, keep_vs), GC, Q + Lx, fac)
+        self._cache.store(key, (kr, keep_vs), GC, Q + Lx, fac, vs)
         return fac, (GC[:, Q:] if Lk else None)
 
     def _kr_solve(self, kr: KhatriRao, fac, C, Xm, ldx, Lk, L, n_total):
@@ -294,7 +317,7 @@ class GP(nn.Module):
             return (KhatriRaoFactor("U", kr, vs, fac), KhatriRaoFactor("UBi", kr, vs, fac),
                     LazySingularValues(self._cache.G, kr.p * kr.q, vs))
         Vm, ldv, Q, Qtrue = self._cat(Vs, vs)
-        fac, _ = self._factorise(Vm, ldv, Q, vs, want_binv)
+        fac, _, _ = self._factorise(Vm, ldv, Q, vs, want_binv)
         U = LowRankFactor("U", Vm, ldv, Q, Qtrue, vs, fac)
         UBi = LowRankFactor("UBi", Vm, ldv, Q, Qtrue, vs, fac)
         return U, UBi, LazySingularValues(self._cache.G, Qtrue, vs)
@@ -312,10 +335,18 @@ class GP(nn.Module):
         elif isinstance(U, LowRankFactor):
             if n != U.n:
                 raise ValueError(f"X has {n} rows but the factorisation was built for {U.n}")
-            C = ops.atb(U.V, U.ldv, Xm, ldx, n, U.Q, Lk)
+            if ops.planes_supported(n, U.Q, Lk):
+                pV = ops.planes_of(U.V, U.ldv)
+                C = ops.atb_planes(pV, ops.split_planes(Xm, ldx, n, Lk), n, U.Q, Lk)
+            else:
+                pV = None
+                C = ops.atb(U.V, U.ldv, Xm, ldx, n, U.Q, Lk)
             self._all_reduce(C)
             W, scal = ops.solve_w(U.fac, C, Lk, Lk, L, self._n_total(n, X.device))
-            Xb, _ = ops.xb_nll(U.V, U.ldv, Xm, ldx, W, n, U.Q, Lk, scal)
+            if pV is not None:
+                Xb, _ = ops.xb_nll_planes(pV, Xm, ldx, W, n, U.Q, Lk, scal)
+            else:
+                Xb, _ = ops.xb_nll(U.V, U.ldv, Xm, ldx, W, n, U.Q, Lk, scal)
         else:
             # dense tensors, exactly gp.py:42-44: (X - UBi (U^T X)) / vn
             Um, ldu = ops.as_matrix(U, "U")
@@ -352,10 +383,13 @@ class GP(nn.Module):
             raise ValueError("X and V must be on the same device")
         Lk = Xm.shape[1]
         n_total = self._n_total(n, X.device)
-        fac, C = self._factorise(Vm, ldv, Q, vs, want_vb, Xm, ldx, Lk, vs_origin=vs_attached)
+        fac, C, pV = self._factorise(Vm, ldv, Q, vs, want_vb, Xm, ldx, Lk, vs_origin=vs_attached)
         W, scal = ops.solve_w(fac, C, C.stride(0), Lk, L, n_total)
         self._stage("solve:end")
-        Xb, nll = ops.xb_nll(Vm, ldv, Xm, ldx, W, n, Q, Lk, scal)
+        if pV is not None:
+            Xb, nll = ops.xb_nll_planes(pV, Xm, ldx, W, n, Q, Lk, scal)
+        else:
+            Xb, nll = ops.xb_nll(Vm, ldv, Xm, ldx, W, n, Q, Lk, scal)
         self._stage("pass2:end")
         return dict(vs=vs, Vm=Vm, ldv=ldv, Q=Q, Qtrue=Qtrue, n=n, L=L, Lk=Lk, n_total=n_total, fac=fac, W=W,
                     scal=scal, Xb=Xb, nll=nll)

@@ -9,12 +9,19 @@ from typing import Optional, Tuple
 
 import torch
 
+import collections
+
 from . import _lib
-from ._lib import GPP_WANT_BINV, NSCAL, check
+from ._lib import GPP_PLANES_COLSQ, GPP_PLANES_UNIT_BOUND, GPP_WANT_BINV, NSCAL, check
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _guard(t: torch.Tensor):
+    """Make `t`'s device current for the duration of a launch (the C side launches on the current device)."""
+    return torch.cuda.device(t.device)
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -82,9 +89,94 @@ def _check_index(t: torch.Tensor, name: str, device) -> torch.Tensor:
     return t.contiguous()
 
 
+# ----------------------------------------------------------------------------- operand planes
+class Planes:
+    """fp16 hi / lo operand planes of an fp32 matrix (include/gppvae_b200.h, "pre-split operand planes"): an opaque
+    device buffer of gpp_planes_bytes(n, cols), optionally carrying the matrix' exact column sums of squares."""
+
+    def __init__(self, buf: torch.Tensor, n: int, cols: int, colsq: bool):
+        self.buf, self.n, self.cols, self.colsq = buf, n, cols, colsq
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+
+_supported_cache = {}
+
+
+def planes_supported(n: int, Q: int, L: int) -> bool:
+    key = (n >= 512, Q >= 128, L >= 64 or L == 0)
+    if key not in _supported_cache:
+        _supported_cache[key] = bool(_lib.load().gpp_planes_supported(n, Q, L))
+    return _supported_cache[key]
+
+
+class _PlaneRegistry:
+    """Planes of the most recently produced matrices, found again by storage address, layout and version.
+
+    An entry keeps its matrix alive, so the address cannot be recycled for another tensor while the entry exists
+    (`_version` catches in-place updates; writes through `.data` are invisible to it -- call `invalidate()`)."""
+
+    def __init__(self, cap: int = 2):
+        self.cap = cap
+        self.entries = collections.OrderedDict()
+
+    @staticmethod
+    def key(t: torch.Tensor, ld: int):
+        return (t.device.index, t.untyped_storage().data_ptr(), t.storage_offset(), t.shape[0], t.shape[1], ld)
+
+    def put(self, t: torch.Tensor, ld: int, planes: Planes) -> None:
+        k = self.key(t, ld)
+        self.entries.pop(k, None)
+        self.entries[k] = (t._version, planes, t)
+        while len(self.entries) > self.cap:
+            self.entries.popitem(last=False)
+
+    def get(self, t: torch.Tensor, ld: int):
+        e = self.entries.get(self.key(t, ld))
+        if e is not None and e[0] == t._version:
+            return e[1]
+        return None
+
+    def drop_shape(self, device, n: int, cols: int) -> None:
+        """Forget entries of this shape: called before a new matrix of the same shape is allocated, so that last epoch's
+        V (which the caller has usually dropped by then) does not stay resident next to the new one."""
+        for k in [k for k in self.entries if k[0] == device.index and k[3] == n and k[4] == cols]:
+            del self.entries[k]
+
+    def invalidate(self) -> None:
+        self.entries.clear()
+
+
+PLANES = _PlaneRegistry()
+
+
+def split_planes(X: torch.Tensor, ldx: int, n: int, cols: int, colsq: bool = False, unit_bound: bool = False) -> Planes:
+    lib = _lib.load()
+    with _guard(X):
+        buf = _workspace(lib.gpp_planes_bytes(n, cols), X.device)
+        ws = _workspace(lib.gpp_split_workspace_bytes(n, cols) if colsq else 0, X.device)
+        flags = (GPP_PLANES_COLSQ if colsq else 0) | (GPP_PLANES_UNIT_BOUND if unit_bound else 0)
+        check(lib.gpp_split_planes(_p(X), ldx, n, cols, flags, _p(buf), buf.numel(), _p(ws), ws.numel(), _stream(X.device)),
+              "split_planes")
+    return Planes(buf, n, cols, colsq)
+
+
+def planes_of(V: torch.Tensor, ldv: int) -> Planes:
+    """The planes of the dense matrix V (with its column sums of squares): from the registry when V came out of
+    Vmodel.forward (or was split before and has not changed since), else split now and remembered."""
+    pl = PLANES.get(V, ldv)
+    if pl is None:
+        pl = split_planes(V, ldv, V.shape[0], V.shape[1], colsq=True)
+        PLANES.put(V, ldv, pl)
+    return pl
+
+
 def khatri_rao_fwd(xn: torch.Tensor, wn: torch.Tensor, d: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """V (n x p*q) from row-normalised tables; returns a view with the reference's shape (columns are
-    padded internally to a multiple of 4 when p*q is not one, by zero-padding p)."""
+    padded internally to a multiple of 4 when p*q is not one, by zero-padding p).  For matrices large enough for the
+    tensor-core passes the same sweep also writes V's operand planes (kept in `PLANES` for GP.taylor_coeff)."""
     require_cuda_f32(xn, "xn")
     require_cuda_f32(wn, "wn")
     d = _check_index(d, "d", xn.device)
@@ -100,9 +192,22 @@ def khatri_rao_fwd(xn: torch.Tensor, wn: torch.Tensor, d: torch.Tensor, w: torch
         xn_k = torch.zeros(P, p_k, device=xn.device, dtype=torch.float32)
         xn_k[:, :p] = xn.detach()
     n = d.shape[0]
-    V = torch.empty(n, p_k * q, device=xn.device, dtype=torch.float32)
-    check(_lib.load().gpp_khatri_rao_fwd(_p(xn_k), P, p_k, _p(wn.detach().contiguous()), nv, q, _p(d), _p(w), n,
-                                         _p(V), V.stride(0) if n > 0 else p_k * q, _stream()), "khatri_rao_fwd")
+    lib = _lib.load()
+    Qk = p_k * q
+    with _guard(xn):
+        if p_k == p and planes_supported(n, Qk, 0):
+            PLANES.drop_shape(xn.device, n, Qk)
+            V = torch.empty(n, Qk, device=xn.device, dtype=torch.float32)
+            buf = _workspace(lib.gpp_planes_bytes(n, Qk), xn.device)
+            ws = _workspace(lib.gpp_split_workspace_bytes(n, Qk), xn.device)
+            check(lib.gpp_khatri_rao_fwd_planes(_p(xn_k), P, p_k, _p(wn.detach().contiguous()), nv, q, _p(d), _p(w), n,
+                                                _p(V), Qk, _p(buf), buf.numel(), _p(ws), ws.numel(),
+                                                _stream(xn.device)), "khatri_rao_fwd_planes")
+            PLANES.put(V, Qk, Planes(buf, n, Qk, True))
+            return V
+        V = torch.empty(n, Qk, device=xn.device, dtype=torch.float32)
+        check(lib.gpp_khatri_rao_fwd(_p(xn_k), P, p_k, _p(wn.detach().contiguous()), nv, q, _p(d), _p(w), n,
+                                     _p(V), V.stride(0) if n > 0 else Qk, _stream(xn.device)), "khatri_rao_fwd")
     return V[:, :Q] if p_k != p else V
 
 
@@ -129,6 +234,40 @@ def gram_vtz(V: torch.Tensor, ldv: int, X: Optional[torch.Tensor], ldx: int, n: 
     ws = _workspace(lib.gpp_gram_workspace_bytes(n, Q, L), V.device)
     check(lib.gpp_gram_vtz(_p(V), ldv, _p(X), ldx, n, Q, L, _p(GC), Q + L, _p(ws), ws.numel(), _stream()), "gram_vtz")
     return GC
+
+
+def gram_vtz_planes(pV: Planes, pX: Optional[Planes], n: int, Q: int, L: int) -> torch.Tensor:
+    """GC = V^T [V | X] from operand planes; the diagonal of G is V's exact column sums of squares."""
+    lib = _lib.load()
+    dev = pV.buf.device
+    with torch.cuda.device(dev):
+        GC = torch.empty(Q, Q + L, device=dev, dtype=torch.float32)
+        ws = _workspace(lib.gpp_gram_planes_workspace_bytes(n, Q, L), dev)
+        check(lib.gpp_gram_vtz_planes(pV.ptr, pX.ptr if pX is not None else None, n, Q, L, int(pV.colsq), _p(GC), Q + L,
+                                      _p(ws), ws.numel(), _stream(dev)), "gram_vtz_planes")
+    return GC
+
+
+def atb_planes(pA: Planes, pB: Planes, n: int, ka: int, kb: int) -> torch.Tensor:
+    lib = _lib.load()
+    dev = pA.buf.device
+    with torch.cuda.device(dev):
+        out = torch.empty(ka, kb, device=dev, dtype=torch.float32)
+        ws = _workspace(lib.gpp_gram_planes_workspace_bytes(n, ka, kb), dev)
+        check(lib.gpp_atb_planes(pA.ptr, pB.ptr, n, ka, kb, _p(out), kb, _p(ws), ws.numel(), _stream(dev)), "atb_planes")
+    return out
+
+
+def xb_nll_planes(pV: Planes, X, ldx, W, n, Q, L, scal) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    dev = X.device
+    with torch.cuda.device(dev):
+        Xb = torch.empty(n, L, device=dev, dtype=torch.float32)
+        nll = torch.empty(n, 1, device=dev, dtype=torch.float32)
+        ws = _workspace(lib.gpp_xb_planes_workspace_bytes(n, Q, L), dev)
+        check(lib.gpp_xb_nll_planes(pV.ptr, _p(X), ldx, _p(W), W.stride(0), n, Q, L, _p(scal), _p(Xb), L, _p(nll), _p(ws),
+                                    ws.numel(), _stream(dev)), "xb_nll_planes")
+    return Xb, nll
 
 
 def atb(A: torch.Tensor, lda: int, B: torch.Tensor, ldb: int, n: int, ka: int, kb: int) -> torch.Tensor:

@@ -147,6 +147,42 @@ int gpp_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const flo
  * GP.solve() when the caller hands in dense U / UBi tensors.  alpha is a host scalar. */
 int gpp_x_minus_am(const float* X, int64_t ldx, const float* A, int64_t lda, const float* M, int64_t ldm,
                    int64_t n, int32_t k, int32_t m, float alpha, float* out, int64_t ldo, gpp_stream_t stream);
+/* ---------------- pre-split operand planes (the fast form of the two N-long sweeps) ----------------
+ * The tensor cores take fp16 operands; an fp32-accurate product needs every operand as hi + lo (hi = the value rounded
+ * to 11 significant bits, lo = the remainder, one power-of-two scale per matrix).  A `planes` buffer holds that form
+ * of one fp32 matrix ONCE -- same 4 bytes per element -- so that gpp_gram_vtz_planes / gpp_xb_nll_planes stream it
+ * with the copy engine straight into the tensor cores (no conversion inside the GEMM kernels).  The buffer is opaque,
+ * caller-owned, gpp_planes_bytes(n, cols) long, 256-byte aligned; it also carries the matrix' exact column sums of
+ * squares when requested (they become the diagonal of V^T V: gp.py:30's U^T U has an exactly representable
+ * same-sign diagonal that the truncating tensor-core accumulator would otherwise bias).
+ *   gpp_split_planes           X (n x cols, fp32) -> planes.  flags: GPP_PLANES_COLSQ, GPP_PLANES_UNIT_BOUND.
+ *   gpp_khatri_rao_fwd_planes  vmod.py:28-35 writing V (fp32, what Vmodel.forward returns) AND its planes (with
+ *                              column sums of squares) in one sweep.
+ *   gpp_gram_vtz_planes        the contract of gpp_gram_vtz with both operands as planes (planesX may be NULL when L = 0);
+ *                              use_colsq != 0 writes the exact diagonal.
+ *   gpp_atb_planes             out = A^T B (ka x kb) from planes (a further right-hand side on a cached factorisation).
+ *   gpp_xb_nll_planes          the contract of gpp_xb_nll with V as planes (X and W stay fp32; W is split internally). */
+#define GPP_PLANES_COLSQ 1u      /* also accumulate the column sums of squares (fp64, fixed order) */
+#define GPP_PLANES_UNIT_BOUND 2u /* caller guarantees |x| <= 1: skip the magnitude scan */
+size_t gpp_planes_bytes(int64_t n, int32_t cols);
+size_t gpp_split_workspace_bytes(int64_t n, int32_t cols);
+int gpp_split_planes(const float* X, int64_t ldx, int64_t n, int32_t cols, uint32_t flags, void* planes,
+                     size_t planes_bytes, void* workspace, size_t workspace_bytes, gpp_stream_t stream);
+int gpp_khatri_rao_fwd_planes(const float* xn, int64_t P, int32_t p, const float* wn, int64_t nviews, int32_t q,
+                              const int64_t* d, const int64_t* w, int64_t n, float* V, int64_t ldv, void* planes,
+                              size_t planes_bytes, void* workspace, size_t workspace_bytes, gpp_stream_t stream);
+size_t gpp_gram_planes_workspace_bytes(int64_t n, int32_t Q, int32_t L);
+int gpp_gram_vtz_planes(const void* planesV, const void* planesX, int64_t n, int32_t Q, int32_t L, int32_t use_colsq,
+                        float* GC, int64_t ldgc, void* workspace, size_t workspace_bytes, gpp_stream_t stream);
+int gpp_atb_planes(const void* planesA, const void* planesB, int64_t n, int32_t ka, int32_t kb, float* out,
+                   int64_t ldo, void* workspace, size_t workspace_bytes, gpp_stream_t stream);
+size_t gpp_xb_planes_workspace_bytes(int64_t n, int32_t Q, int32_t L);
+int gpp_xb_nll_planes(const void* planesV, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n,
+                      int32_t Q, int32_t L, double* scal, float* Xb, int64_t ldxb, float* nll, void* workspace,
+                      size_t workspace_bytes, gpp_stream_t stream);
+/* 1 when the planes kernels take this shape (n >= 512, Q >= 128), else the fp32 entries must be used */
+int gpp_planes_supported(int64_t n, int32_t Q, int32_t L);
+
 /* out = A^T B   A:(n x ka) B:(n x kb) -> (ka x kb).  Generic form of gp.py:42 (U^T X). */
 size_t gpp_atb_workspace_bytes(int64_t n, int32_t ka, int32_t kb);
 int gpp_atb(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int32_t ka, int32_t kb,

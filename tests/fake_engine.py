@@ -149,10 +149,14 @@ class _TaylorExpansion:
         return out + (vbs * torch.softmax(lvs, 0)).sum() / float(X.shape[0])
 
 
+def planes_supported(n, Q, L):
+    return False     # the operand-plane kernels are tensor-core code: the stand-in always takes the fp32 entries
+
+
 def install(monkeypatch):
     for name in ("normalize_rows", "_KhatriRao", "_TaylorExpansion"):
         monkeypatch.setattr(real_ops, name, globals()[name])
     for name in ("as_matrix", "gram_vtz", "atb", "factor", "solve_w", "xb_nll", "vbs_from_scal", "vb",
                  "require_cuda_f32", "_check_index", "khatri_rao_fwd", "kr_slot_sums", "kr_assemble_gc", "kr_assemble_m",
-                 "am", "kr_xb_nll"):
+                 "am", "kr_xb_nll", "planes_supported"):
         monkeypatch.setattr(real_ops, name, globals()[name])
