@@ -174,10 +174,10 @@ def qspace_model(X: Tensor, V: Tensor, lvs: Tensor, n_total: int | None = None, 
         Q = V.shape[1]
         G = V.t().mm(V)
         C = V.t().mm(X)
-        B = torch.eye(Q, dtype=V.dtype) + r * G
+        B = torch.eye(Q, dtype=V.dtype, device=V.device) + r * G
         Lc = torch.linalg.cholesky(B)
         logdetB = 2.0 * Lc.diagonal().log().sum()
-        Linv = torch.linalg.solve_triangular(Lc, torch.eye(Q, dtype=V.dtype), upper=False)
+        Linv = torch.linalg.solve_triangular(Lc, torch.eye(Q, dtype=V.dtype, device=V.device), upper=False)
         Binv = Linv.t().mm(Linv)
         W = r * Binv.mm(C)
         Xb = (X - V.mm(W)) / vn
@@ -193,3 +193,41 @@ def qspace_model(X: Tensor, V: Tensor, lvs: Tensor, n_total: int | None = None, 
         if want_vb:
             out["Vb"] = r * L * V.mm(Binv) - Xb.mm(W.t())
     return out
+
+
+def qspace_model_streamed(X: Tensor, V: Tensor, lvs: Tensor, n_total: int | None = None, chunk: int = 1 << 16):
+    """qspace_model() in float64 for inputs too large to hold as doubles: X and V (any float dtype, any device) are
+    read in row chunks converted to float64 on the fly, so a 16 GB fp32 V never needs a 32 GB copy.  Same formulas,
+    same outputs except the N x Q ones (no Vb, no G-sized extras beyond G itself).  This is the checker of the
+    full-size GPU parity tests (BASELINE.json configs[1], configs[2]): it runs on the GPU box's device through stock
+    torch float64 -- test infrastructure, never the product path."""
+    with torch.no_grad():
+        dev = V.device
+        vs = variances(lvs.to(device=dev, dtype=torch.float64))
+        v0, vn = vs[0], vs[1]
+        r = v0 / vn
+        n, L = X.shape
+        n_total = n if n_total is None else n_total
+        Q = V.shape[1]
+        G = torch.zeros(Q, Q, dtype=torch.float64, device=dev)
+        C = torch.zeros(Q, L, dtype=torch.float64, device=dev)
+        for a in range(0, n, chunk):
+            Vc = V[a:a + chunk].double()
+            G.addmm_(Vc.t(), Vc)
+            C.addmm_(Vc.t(), X[a:a + chunk].double())
+        B = torch.eye(Q, dtype=torch.float64, device=dev) + r * G
+        Lc = torch.linalg.cholesky(B)
+        logdetB = 2.0 * Lc.diagonal().log().sum()
+        Binv = torch.cholesky_inverse(Lc)
+        W = r * Binv.mm(C)
+        Xb = torch.empty(n, L, dtype=torch.float64, device=dev)
+        for a in range(0, n, chunk):
+            Xb[a:a + chunk] = (X[a:a + chunk].double() - V[a:a + chunk].double().mm(W)) / vn
+        quad = (X.double() * Xb).sum(1, keepdim=True)
+        row_const = 0.5 * L * (vn.log() + logdetB / n_total)
+        trBinv = Binv.diagonal().sum()
+        vbs = torch.stack([
+            -0.5 * (W * W).sum() / (v0 * v0) + 0.5 * L * ((Q - trBinv) / r) / vn,
+            -0.5 * (Xb * Xb).sum() + 0.5 * L * (n_total - Q + trBinv) / vn,
+        ])
+        return dict(G=G, C=C, logdetB=logdetB, W=W, Xb=Xb, nll=0.5 * quad + row_const, vbs=vbs, trBinv=trBinv)

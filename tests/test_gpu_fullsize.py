@@ -1,0 +1,107 @@
+"""Full-size GPU parity (BASELINE.json configs[1] = c2 and configs[2] = c3, the configuration the headline number is
+quoted on): the CUDA path through the drop-in classes against
+
+  * c2 (N=100k, Q=1024, L=256): the CPU oracle's taylor_coeff (oracle/gp_oracle.py, the restatement of gp.py:55-95) in
+    float32 (= the reference as shipped) and float64 (= ground truth), on the host cores;
+  * c3 (N=1M, Q=4096, L=256) and N=250k at the same Q: the oracle's Q-space model in float64, streamed over the rows
+    on the device with stock torch as the CHECKER (a float64 CPU run of the reference at this size needs ~100 GB and
+    hours) -- trained-like and init-like tables, lvs = (0, 0) and (2, -4).
+
+Tolerances are BASELINE.json's: relative error of sum(nll) <= 1e-5, max-relative error of dNLL/dZ (= Xb) <= 1e-4.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NLL_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+def _ours(pr, cfg, dev, need_vb=False):
+    import gppvae_b200
+    vm = gppvae_b200.Vmodel(pr.x0.shape[0], cfg["q"], cfg["p"], cfg["q"]).to(dev)
+    gp = gppvae_b200.GP().to(dev)
+    with torch.no_grad():
+        vm.x0.copy_(pr.x0); vm.v0.copy_(pr.v0); gp.lvs.copy_(pr.lvs)
+        V = vm(pr.d, pr.w)
+        out = gp.taylor_coeff(pr.Z, [V], need_vb=need_vb)
+    return V, out, gp
+
+
+@pytest.mark.parametrize("kind,lvs", [("trained", (0.0, 0.0)), ("init", (0.0, 0.0)), ("trained", (2.0, -4.0))])
+def test_c2_against_cpu_oracle(dev, kind, lvs):
+    """configs[1] at full size against oracle.taylor_coeff (gp.py:55-95) in float32 and float64 on the CPU."""
+    from gppvae_b200.synth import CONFIGS, make_problem
+    from oracle import gp_oracle as O
+    cfg = CONFIGS["c2"]
+    pr = make_problem(cfg["N"], cfg["p"], cfg["q"], cfg["L"], kind=kind, lvs=lvs, seed=11, device=dev)
+    V, (Xb, _, vbs, nll), _ = _ours(pr, cfg, dev)
+    torch.cuda.synchronize()
+    x0, v0, d, w, Z, l = (t.cpu() for t in (pr.x0, pr.v0, pr.d, pr.w, pr.Z, pr.lvs))
+    # ground truth: the reference algorithm in float64
+    V64 = O.feature_map(x0.double(), v0.double(), d, w)
+    nll64, Xb64 = O.nll_and_grad(Z.double(), [V64], l.double())
+    # the reference as shipped: float32
+    V32 = O.feature_map(x0, v0, d, w)
+    nll32, Xb32 = O.nll_and_grad(Z, [V32], l)
+    s64 = nll64.sum().item()
+    e_nll = abs(nll.double().sum().item() - s64) / abs(s64)
+    e_xb = _rel(Xb.cpu(), Xb64)
+    ref_nll = abs(nll32.double().sum().item() - s64) / abs(s64)
+    ref_xb = _rel(Xb32, Xb64)
+    print(f"c2 {kind} lvs={lvs}: ours vs fp64: nll {e_nll:.2e} Xb {e_xb:.2e}   [fp32 reference vs fp64: nll {ref_nll:.2e} "
+          f"Xb {ref_xb:.2e}]   ours vs fp32 reference: nll "
+          f"{abs(nll.double().sum().item() - nll32.double().sum().item()) / abs(s64):.2e} Xb {_rel(Xb.cpu(), Xb32):.2e}")
+    assert _rel(V.cpu(), V64) < 1e-6
+    assert e_nll <= NLL_TOL
+    assert e_xb <= GRAD_TOL
+    # against the fp32 reference itself, allowing for that reference's own distance from the truth
+    assert abs(nll.double().sum().item() - nll32.double().sum().item()) / abs(s64) <= NLL_TOL + ref_nll
+    assert _rel(Xb.cpu(), Xb32) <= GRAD_TOL + ref_xb
+
+
+def _streamed_case(dev, N, kind, lvs, tag):
+    from gppvae_b200.synth import CONFIGS, make_problem
+    from oracle import gp_oracle as O
+    cfg = dict(CONFIGS["c3"], N=N)
+    pr = make_problem(N, cfg["p"], cfg["q"], cfg["L"], kind=kind, lvs=lvs, seed=7, device=dev)
+    V, (Xb, _, vbs, nll), gp = _ours(pr, cfg, dev)
+    ref = O.qspace_model_streamed(pr.Z, V, pr.lvs)
+    s64 = ref["nll"].sum().item()
+    e_nll = abs(nll.double().sum().item() - s64) / abs(s64)
+    e_xb = _rel(Xb, ref["Xb"])
+    e_vbs = _rel(vbs, ref["vbs"])
+    # the diagonal of G is the exactly accumulated column sums of squares: correctly rounded fp32
+    G = gp._cache.G[:, : V.shape[1]]
+    e_diag = float(((G.diagonal().double() - ref["G"].diagonal()).abs() / ref["G"].diagonal().abs()).max())
+    e_g = _rel(G, ref["G"])
+    print(f"{tag} N={N} {kind} lvs={lvs}: nll {e_nll:.2e}  Xb {e_xb:.2e}  vbs {e_vbs:.2e}  G {e_g:.2e}  diag(G) {e_diag:.2e}")
+    assert e_diag <= 6.1e-8
+    assert e_nll <= NLL_TOL
+    assert e_xb <= GRAD_TOL
+    del ref, V, Xb, nll, pr
+    gp.invalidate_cache()
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("kind,lvs", [("trained", (0.0, 0.0)), ("init", (0.0, 0.0)), ("trained", (2.0, -4.0)),
+                                      ("init", (2.0, -4.0))])
+def test_c3_against_fp64_qspace_model(dev, kind, lvs):
+    """configs[2] -- the headline configuration -- at full size (N=1M, Q=4096, L=256)."""
+    _streamed_case(dev, 1_000_000, kind, lvs, "c3")
+
+
+def test_quarter_c3_no_drift_with_n(dev):
+    """The same check at N=250k, Q=4096: the error level must not depend on the number of rows accumulated."""
+    _streamed_case(dev, 250_000, "trained", (0.0, 0.0), "c3/4")
+    _streamed_case(dev, 250_000, "init", (2.0, -4.0), "c3/4")
