@@ -34,7 +34,13 @@ using namespace tc;
 
 namespace {
 
-constexpr int PBK = 64;                     // k-rows per stage = one accumulation window
+constexpr int PBK = 64;                     // k-rows per stage
+#ifndef GPP_PL_WIN
+#define GPP_PL_WIN 64
+#endif
+constexpr int kWin = GPP_PL_WIN;            // k-rows per accumulation window in TMEM (16, 32 or 64)
+constexpr int kSub = PBK / kWin;            // windows per stage
+static_assert(kWin == 16 || kWin == 32 || kWin == 64, "window length");
 constexpr int kPlStages = 3;
 constexpr int kBoxBytes = 64 * 128;         // {64 halfs, 64 rows}
 constexpr int kPlStageBytes = 8 * kBoxBytes;
@@ -93,18 +99,15 @@ __device__ __forceinline__ void pl_epilogue(uint32_t tmem) {
   if ((threadIdx.x >> 5) == 1) tmem_dealloc_pair(tmem, 512);
 }
 
-// One window (= one stage, 64 k-rows) of a 256 x 256 tile: correction terms of the four K = 16 steps first (into the
-// still-small accumulator), the hi.hi terms last; then the stage goes back to the producers and the accumulator to the
-// drain warps.  A_KMAJOR: A boxes are {64 halfs of k, 128 rows} (row GEMM), else MN-major like B (pass 1).
+// One stage (64 k-rows) of a 256 x 256 tile, as kSub accumulation windows of kWin rows: inside a window the correction
+// terms of its K = 16 steps first (into the still-small accumulator), the hi.hi terms last; every window goes to the
+// drain warps through the next of the two TMEM accumulators, and after the last one the stage goes back to the producers.
+// A_KMAJOR: A boxes are {64 halfs of k, 128 rows} (row GEMM), else MN-major like B (pass 1).  w: windows issued so far.
 template <bool A_KMAJOR>
-__device__ __forceinline__ void issue_window(uint8_t* base, PlShared* sm, uint32_t tmem, uint32_t it, uint32_t w) {
+__device__ __forceinline__ void issue_stage(uint8_t* base, PlShared* sm, uint32_t tmem, uint32_t it, uint32_t& w) {
   constexpr uint32_t idesc = umma_idesc_f16(kTileM, kTileN, !A_KMAJOR, true);
-  const int s = it % kPlStages, buf = w & 1;
-  mbar_wait_cluster(&sm->tempty[buf], ((w >> 1) & 1) ^ 1);   // drain warps of both CTAs are done with this accumulator
-  mbar_wait(&sm->full[s], (it / kPlStages) & 1);             // both CTAs' boxes have landed
-  tcgen05_fence_after();
+  const int s = it % kPlStages;
   const uint32_t sb = smem_u32(base + s * kPlStageBytes);
-  const uint32_t d = tmem + buf * 256;
   const uint32_t ah = sb, al = sb + 2 * kBoxBytes, bh = sb + 4 * kBoxBytes, bl = sb + 6 * kBoxBytes;
   // MN-major SWIZZLE_128B: 64-column groups kBoxBytes apart (LBO), 8-row k-groups 1 KB apart (SBO), K = 16 -> +2 KB;
   // K-major SWIZZLE_128B: 8-row groups 1 KB apart (SBO), K = 16 -> +32 B inside the 128-byte row
@@ -113,31 +116,75 @@ __device__ __forceinline__ void issue_window(uint8_t* base, PlShared* sm, uint32
   };
   auto bdesc = [&](uint32_t b0, int kk) { return umma_desc(b0 + kk * 2048, kBoxBytes, 1024, kLayoutSw128); };
 #pragma unroll
-  for (int kk = 0; kk < PBK / 16; ++kk) {
-    umma_f16_pair_ss(d, adesc(ah, kk), bdesc(bl, kk), idesc, kk > 0);
-    umma_f16_pair_ss(d, adesc(al, kk), bdesc(bh, kk), idesc, 1);
-  }
+  for (int sw = 0; sw < kSub; ++sw, ++w) {
+    const int buf = w & 1;
+    mbar_wait_cluster(&sm->tempty[buf], ((w >> 1) & 1) ^ 1);   // drain warps of both CTAs are done with this accumulator
+    if (sw == 0) mbar_wait(&sm->full[s], (it / kPlStages) & 1);  // both CTAs' boxes have landed
+    tcgen05_fence_after();
+    const uint32_t d = tmem + buf * 256;
+    constexpr int kSteps = kWin / 16;
 #pragma unroll
-  for (int kk = 0; kk < PBK / 16; ++kk) umma_f16_pair_ss(d, adesc(ah, kk), bdesc(bh, kk), idesc, 1);
-  umma_commit_pair(&sm->empty[s], 3);
-  umma_commit_pair(&sm->tfull[buf], 3);
+    for (int k = 0; k < kSteps; ++k) {
+      const int kk = sw * kSteps + k;
+      umma_f16_pair_ss(d, adesc(ah, kk), bdesc(bl, kk), idesc, k > 0);
+      umma_f16_pair_ss(d, adesc(al, kk), bdesc(bh, kk), idesc, 1);
+    }
+#pragma unroll
+    for (int k = 0; k < kSteps; ++k) {
+      const int kk = sw * kSteps + k;
+      umma_f16_pair_ss(d, adesc(ah, kk), bdesc(bh, kk), idesc, 1);
+    }
+    if (sw == kSub - 1) umma_commit_pair(&sm->empty[s], 3);
+    umma_commit_pair(&sm->tfull[buf], 3);
+  }
 }
 
-// Drain warps (4-11): add window w (this CTA's 128 rows x this warp's 128 columns) into registers.
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread, no wait (pair with tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// acc (two packed fp32) += {lo, hi}, round-to-nearest: one FADD2 for two accumulator columns
+__device__ __forceinline__ void add2(unsigned long long& acc, uint32_t lo, uint32_t hi) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(v));
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  return make_float2(__uint_as_float(lo), __uint_as_float(hi));
+}
+
+// Drain warps (4-11): add window w (this CTA's 128 rows x this warp's 128 columns) into registers (packed pairs).
 __device__ __forceinline__ void drain_window(PlShared* sm, uint32_t tmem, uint32_t tempty0_leader, uint32_t w,
-                                             float (&acc)[128]) {
+                                             unsigned long long (&acc)[64]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int buf = w & 1;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   const int cb = (warp - 4) >> 2;
   mbar_wait(&sm->tfull[buf], (w >> 1) & 1);
   tcgen05_fence_after();
+  const uint32_t t0 = tmem + lane_addr + buf * 256 + cb * 128;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float v[32];
-    tmem_ld_32x32(tmem + lane_addr + buf * 256 + cb * 128 + c * 32, v);
+  for (int c = 0; c < 4; c += 2) {
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32_nowait(t0 + c * 32, v0);
+    tmem_ld_32x32_nowait(t0 + c * 32 + 32, v1);
+    tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[c * 32 + j] += v[j];
+    for (int j = 0; j < 16; ++j) add2(acc[c * 16 + j], v0[2 * j], v0[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) add2(acc[c * 16 + 16 + j], v1[2 * j], v1[2 * j + 1]);
   }
   tcgen05_fence_before();
   __syncwarp();
@@ -209,13 +256,13 @@ pl_pass1_kernel(const __grid_constant__ CUtensorMap tmVh, const __grid_constant_
       }
     } else if (warp == 1 && lane == 0 && rank == 0) {
       // ===================================================== MMA issuer (leader CTA)
-      uint32_t it = 0;
+      uint32_t it = 0, w = 0;
       for (int u = pair; u < nunits; u += npairs) {
         const int split = u / p.tiles;
         const int64_t r0 = (int64_t)split * p.rows_per_split;
         const int64_t r1 = min(p.n, r0 + p.rows_per_split);
         const int nst = (int)((r1 - r0 + PBK - 1) / PBK);
-        for (int st = 0; st < nst; ++st, ++it) issue_window<false>(base, sm, tmem, it, it);
+        for (int st = 0; st < nst; ++st, ++it) issue_stage<false>(base, sm, tmem, it, w);
       }
     }
   } else {
@@ -231,16 +278,18 @@ pl_pass1_kernel(const __grid_constant__ CUtensorMap tmVh, const __grid_constant_
       const int64_t r0 = (int64_t)split * p.rows_per_split;
       const int64_t r1 = min(p.n, r0 + p.rows_per_split);
       const int nst = (int)((r1 - r0 + PBK - 1) / PBK);
-      float acc[128];
+      unsigned long long acc[64];
 #pragma unroll
-      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-      for (int st = 0; st < nst; ++st, ++w) drain_window(sm, tmem, tempty0, w, acc);
+      for (int i = 0; i < 64; ++i) acc[i] = 0ull;
+      for (int st = 0; st < nst * kSub; ++st, ++w) drain_window(sm, tmem, tempty0, w, acc);
       const float os = tile < p.tiles_g ? out_g : out_c;   // undo the common power-of-two scale of the split (exact)
       float* out = p.partial + ((size_t)tile * p.splits + split) * (size_t)(kTileM * kTileN) +
                    (size_t)(rank * 128 + q * 32 + lane) * kTileN + cb * 128;
 #pragma unroll
-      for (int i = 0; i < 128; i += 4)
-        *reinterpret_cast<float4*>(out + i) = make_float4(os * acc[i], os * acc[i + 1], os * acc[i + 2], os * acc[i + 3]);
+      for (int i = 0; i < 64; i += 2) {
+        const float2 a = unpack2(acc[i]), b = unpack2(acc[i + 1]);
+        *reinterpret_cast<float4*>(out + 2 * i) = make_float4(os * a.x, os * a.y, os * b.x, os * b.y);
+      }
     }
   }
   pl_epilogue(tmem);
@@ -314,9 +363,9 @@ pl_rows_kernel(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant_
         }
       }
     } else if (warp == 1 && lane == 0 && rank == 0) {
-      uint32_t it = 0;
+      uint32_t it = 0, w = 0;
       for (int64_t u = pair; u < nunits; u += npairs)
-        for (int st = 0; st < nst; ++st, ++it) issue_window<true>(base, sm, tmem, it, it);
+        for (int st = 0; st < nst; ++st, ++it) issue_stage<true>(base, sm, tmem, it, w);
     }
   } else {
     setmaxnreg_inc<216>();
@@ -331,10 +380,17 @@ pl_rows_kernel(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant_
     for (int64_t u = pair; u < nunits; u += npairs) {
       const int64_t rt = u / p.col_tiles;
       const int ct = (int)(u - rt * p.col_tiles);
+      unsigned long long acc2[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc2[i] = 0ull;
+      for (int st = 0; st < nst * kSub; ++st, ++w) drain_window(sm, tmem, tempty0, w, acc2);
       float acc[128];
 #pragma unroll
-      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-      for (int st = 0; st < nst; ++st, ++w) drain_window(sm, tmem, tempty0, w, acc);
+      for (int i = 0; i < 64; ++i) {
+        const float2 a = unpack2(acc2[i]);
+        acc[2 * i] = a.x;
+        acc[2 * i + 1] = a.y;
+      }
       const int64_t row = rt * kTileM + rank * 128 + q * 32 + lane;
       const int col0 = ct * kTileN + cb * 128;
       float xb2 = 0.f;
@@ -468,29 +524,53 @@ kr_planes_kernel(const float* __restrict__ xn, int64_t P, int p, const float* __
   const float qnan = __int_as_float(0x7fc00000);
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(n, r0 + rows_per_block);
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll 4
-  for (int64_t r = r0; r < r1; ++r) {
-    const int64_t di = d[r], wi = w[r];
-    const bool ok = (di >= 0) & (di < P) & (wi >= 0) & (wi < nviews);
-    float4 v = make_float4(qnan, qnan, qnan, qnan);
-    if (ok) {
-      const float* xr = xn + di * p;
-      const float* wr = wn + wi * q;
+  // Rows in batches of kB: all index loads of a batch, then all table loads, then the stores -- the two dependent
+  // gathers per row are what bounds this kernel, so keep kB of them in flight per thread; the indices of the next batch
+  // are fetched behind the stores of this one.
+  constexpr int kB = 4;
+  int64_t di[kB], wi[kB];
+#pragma unroll
+  for (int u = 0; u < kB; ++u) {
+    const int64_t r = min(r0 + u, r1 - 1);
+    di[u] = d[r];
+    wi[u] = w[r];
+  }
+  for (int64_t rb = r0; rb < r1; rb += kB) {
+    float4 v[kB];
+#pragma unroll
+    for (int u = 0; u < kB; ++u) {
+      const bool ok = (di[u] >= 0) & (di[u] < P) & (wi[u] >= 0) & (wi[u] < nviews);
+      const float* xr = xn + (ok ? di[u] : 0) * p;
+      const float* wr = wn + (ok ? wi[u] : 0) * q;
+      float4 t;
       if (quad) {
         const float x = xr[j[0]];
         const float4 w4 = *reinterpret_cast<const float4*>(wr + k[0]);
-        v = make_float4(x * w4.x, x * w4.y, x * w4.z, x * w4.w);
+        t = make_float4(x * w4.x, x * w4.y, x * w4.z, x * w4.w);
       } else {
-        v = make_float4(xr[j[0]] * wr[k[0]], xr[j[1]] * wr[k[1]], xr[j[2]] * wr[k[2]], xr[j[3]] * wr[k[3]]);
+        t = make_float4(xr[j[0]] * wr[k[0]], xr[j[1]] * wr[k[1]], xr[j[2]] * wr[k[2]], xr[j[3]] * wr[k[3]]);
+      }
+      v[u] = ok ? t : make_float4(qnan, qnan, qnan, qnan);
+    }
+#pragma unroll
+    for (int u = 0; u < kB; ++u) {   // next batch's indices
+      const int64_t r = min(rb + kB + u, r1 - 1);
+      di[u] = d[r];
+      wi[u] = w[r];
+    }
+#pragma unroll
+    for (int u = 0; u < kB; ++u) {
+      const int64_t r = rb + u;
+      if (r < r1) {
+        *reinterpret_cast<float4*>(V + r * ldv + c) = v[u];
+        uint2 h, l;
+        split4(v[u], sc, h, l);
+        *reinterpret_cast<uint2*>(H + r * ldp + c) = h;
+        *reinterpret_cast<uint2*>(Lo + r * ldp + c) = l;
+        s0 = fma((double)v[u].x, (double)v[u].x, s0); s1 = fma((double)v[u].y, (double)v[u].y, s1);
+        s2 = fma((double)v[u].z, (double)v[u].z, s2); s3 = fma((double)v[u].w, (double)v[u].w, s3);
       }
     }
-    *reinterpret_cast<float4*>(V + r * ldv + c) = v;
-    uint2 h, l;
-    split4(v, sc, h, l);
-    *reinterpret_cast<uint2*>(H + r * ldp + c) = h;
-    *reinterpret_cast<uint2*>(Lo + r * ldp + c) = l;
-    s0 = fma((double)v.x, (double)v.x, s0); s1 = fma((double)v.y, (double)v.y, s1);
-    s2 = fma((double)v.z, (double)v.z, s2); s3 = fma((double)v.w, (double)v.w, s3);
   }
   double* o = colsq_part + (int64_t)blockIdx.y * cols + c;
   o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;

@@ -420,7 +420,7 @@ class GP(nn.Module):
     def nll(self, X: torch.Tensor, Vs: Sequence[torch.Tensor]) -> torch.Tensor:
         """gp.py:97-110.  Differentiable: backward applies the Taylor coefficients (the exact gradients
         of sum(nll), gp.py:185-221), i.e. it is exact for a uniform upstream gradient (`.sum()`,
-        `.mean()`) -- the only way the reference ever differentiates it."""
+        `.mean()`) -- the only way the reference ever differentiates it; any other upstream gradient raises."""
         return _NllFunction.apply(self, X, self.lvs, *Vs)
 
     def nll_ineff(self, X: torch.Tensor, Vs: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -440,13 +440,26 @@ class GP(nn.Module):
 
 
 class _NllFunction(torch.autograd.Function):
+    """gp.py:97-110 with the Taylor coefficients as its backward.
+
+    The coefficients are the exact gradients of sum_i nll_i (gp.py:185-221).  nll_i couples all rows through K^-1, so a
+    NON-uniform upstream gradient (a weighted sum of the rows) has a different gradient, which this class does not
+    implement: it raises instead of returning the uniform-weight one.  `.sum()`, `.mean()` and any constant multiple --
+    every way the reference ever differentiates nll -- are exact."""
+
     @staticmethod
     def forward(ctx, gp: GP, X, lvs, *Vs):
         want_grad = any(ctx.needs_input_grad[1:])
+        dense = [torch.is_tensor(V) for V in Vs]
+        ctx.dense = dense
         with torch.no_grad():
             if want_grad:
-                Xb, Vbs, vbs, nll = gp.taylor_coeff(X, list(Vs))
-                ctx.save_for_backward(Xb, vbs, gp.get_vs().detach(), *Vbs)
+                # a factored V (vmod.KhatriRao) is a detached snapshot: no gradient flows to it, its Vb is never formed
+                need_vb = any(d and ng for d, ng in zip(dense, ctx.needs_input_grad[3:]))
+                Xb, Vbs, vbs, nll = gp.taylor_coeff(X, list(Vs), need_vb=need_vb)
+                saved = [Vb for Vb, d in zip(Vbs, dense) if d and torch.is_tensor(Vb)]
+                ctx.n_vb = len(saved)
+                ctx.save_for_backward(Xb, vbs, gp.get_vs().detach(), *saved)
             else:
                 nll = gp._coefficients(X, list(Vs), False)["nll"]
         return nll
@@ -454,8 +467,17 @@ class _NllFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         Xb, vbs, vs, *Vbs = ctx.saved_tensors
-        gbar = g.mean()   # exact for a uniform upstream gradient (see GP.nll)
+        gmin, gmax = torch.aminmax(g.detach())
+        gbar = float(gmax)
+        if float(gmin) != gbar:
+            raise NotImplementedError(
+                "GP.nll: backward is implemented for a uniform upstream gradient only (nll.sum(), nll.mean(), or a "
+                "constant multiple); a per-row weighting couples the rows through K^-1 and needs a second solve")
         gX = gbar * Xb if ctx.needs_input_grad[1] else None
         glvs = gbar * vs * (vbs - (vbs * vs).sum()) if ctx.needs_input_grad[2] else None
-        gVs = tuple(gbar * Vb if need else None for Vb, need in zip(Vbs, ctx.needs_input_grad[3:]))
+        it = iter(Vbs)
+        gVs = []
+        for d, need in zip(ctx.dense, ctx.needs_input_grad[3:]):
+            Vb = next(it) if (d and ctx.n_vb) else None
+            gVs.append(gbar * Vb if (need and Vb is not None) else None)
         return (None, gX, glvs, *gVs)

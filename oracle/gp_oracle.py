@@ -75,7 +75,7 @@ def woodbury_factor(Vs: Sequence[Tensor], vs: Tensor) -> Tuple[Tensor, Tensor, T
     """``U, U B^-1, svdvals(B)`` with ``B = U^T U + I`` (reference gp.py:24-38)."""
     stacked = torch.cat([vs[i].sqrt() * Vi for i, Vi in enumerate(Vs)], 1)   # gp.py:27
     U = stacked / vs[-1].sqrt()                                               # gp.py:28
-    B = U.t().mm(U) + torch.eye(U.shape[1], dtype=U.dtype)                    # gp.py:29-30
+    B = U.t().mm(U) + torch.eye(U.shape[1], dtype=U.dtype, device=U.device)  # gp.py:29-30
     Shb = torch.svd(B)[1]                                                     # gp.py:33
     UBi = U.mm(torch.inverse(B))                                              # gp.py:35-36
     return U, UBi, Shb

@@ -1,6 +1,6 @@
-"""Host-side restatement (numpy) of the operand split the tensor-core data passes use (gppvae_b200/csrc/gemm_tc.cu:
-hi11<true>, make_scales<true>, the fp16 packing of the converters): checks the error bounds DESIGN.md 5.1 states for
-it, independent of any GPU.  A specification test of the arithmetic, not of the kernels (those are covered by the
+"""Host-side restatement (numpy) of the operand split the tensor-core data passes use (gppvae_b200/csrc/pass1_common.cuh
+hi11_round / kF16Top, gemm_planes.cu split4; the converters of gemm_tc.cu use the same arithmetic): checks the error
+bounds DESIGN.md 5.1 states for it, independent of any GPU.  A specification test of the arithmetic, not of the kernels (those are covered by the
 `-m gpu` parity tests)."""
 import numpy as np
 import pytest
@@ -73,8 +73,9 @@ def test_hi_is_exactly_an_fp16_number_and_lo_is_zero_mean():
     assert abs((lo / x)[big].mean()) < 2.0 ** -11 / 50                                      # zero-mean remainder
 
 
-def test_headroom_above_the_sampled_maximum():
-    """An element up to 2^8 above the maximum the scale was derived from still converts without saturating."""
+def test_headroom_above_the_maximum():
+    """The scale is derived from the exact maximum, so nothing can exceed it; the format itself still leaves 2^8 of
+    headroom (an element up to 2^8 above the maximum the scale was derived from converts without saturating)."""
     x = np.array([1.0, 0.3, -0.9], dtype=np.float32)
     e = exp_of_max(x)                                   # 2^0 <= 1.0 < 2^1  ->  e = 1
     outlier = np.array([250.0 * 2.0 ** (e - 1)], dtype=np.float32)
