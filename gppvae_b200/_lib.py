@@ -81,6 +81,9 @@ _SIGNATURES = {
                                          c_int64, _PF, c_int64, _PF, c_void_p]),
     "gpp_host_ctx_create": (c_int, [ctypes.POINTER(c_void_p)]),
     "gpp_host_ctx_destroy": (c_int, [c_void_p]),
+    "gpp_gp_term_host_submit": (c_int, [c_void_p, _PF, c_int64, c_int32, _PF, c_int64, c_int32, _PF, _PF, _PF, c_int64,
+                                        c_int32, _PF, _PF, _PF, _PF, ctypes.POINTER(c_int32)]),
+    "gpp_gp_term_host_wait": (c_int, [c_void_p, c_int32]),
     "gpp_gp_term_host": (c_int, [c_void_p, _PF, c_int64, c_int32, _PF, c_int64, c_int32, _PF, _PF, _PF, c_int64,
                                  c_int32, _PF, _PF, _PF, _PF]),
 }

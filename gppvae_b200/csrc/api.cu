@@ -294,19 +294,35 @@ __global__ void softmax2_kernel(const float* __restrict__ lvs, float* __restrict
 }
 }  // namespace gpp
 
+// The host-buffer entry overlaps the PCIe copies with the compute they do not feed:
+//   copy-in stream : X (the N x L latent matrix, the only large input) -> device
+//   compute stream : tables, indices, Khatri-Rao map + planes, the Gram tiles of pass 1 and the Cholesky -- none of which
+//                    needs X -- then (after the copy-in event) split X, V^T X, W, pass 2
+//   copy-out stream: nll, Xb, vbs -> host, behind the compute of the NEXT submission (two host-facing buffer sets)
+// gpp_gp_term_host_submit / _wait expose that pipeline; gpp_gp_term_host = submit + wait.
 struct gpp_host_ctx {
-  cudaStream_t stream = nullptr;
+  cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+  bool out_pending[2] = {false, false}, used[2] = {false, false};
   void* arena = nullptr;
   size_t arena_bytes = 0;
+  unsigned next = 0;
 };
 
 extern "C" int gpp_host_ctx_create(gpp_host_ctx** ctx) {
   GPP_REQUIRE(ctx, "host_ctx_create: null");
   gpp_host_ctx* c = new gpp_host_ctx();
-  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  cudaError_t e = cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&c->in_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->comp_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
-    delete c;
-    set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    gpp_host_ctx_destroy(c);
+    set_error("host_ctx_create: %s", cudaGetErrorString(e));
     return GPP_ERR_CUDA;
   }
   *ctx = c;
@@ -315,25 +331,47 @@ extern "C" int gpp_host_ctx_create(gpp_host_ctx** ctx) {
 
 extern "C" int gpp_host_ctx_destroy(gpp_host_ctx* ctx) {
   if (!ctx) return GPP_OK;
+  if (ctx->compute) cudaStreamSynchronize(ctx->compute);
+  if (ctx->copy_out) cudaStreamSynchronize(ctx->copy_out);
   if (ctx->arena) cudaFree(ctx->arena);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->in_done[i]) cudaEventDestroy(ctx->in_done[i]);
+    if (ctx->comp_done[i]) cudaEventDestroy(ctx->comp_done[i]);
+    if (ctx->out_done[i]) cudaEventDestroy(ctx->out_done[i]);
+  }
+  if (ctx->compute) cudaStreamDestroy(ctx->compute);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   delete ctx;
   return GPP_OK;
 }
 
-extern "C" int gpp_gp_term_host(gpp_host_ctx* ctx, const float* x0_host, int64_t P, int32_t p, const float* v0_host,
-                                int64_t nviews, int32_t q, const int64_t* d_host, const int64_t* w_host,
-                                const float* X_host, int64_t n, int32_t L, const float* lvs_host, float* nll_host,
-                                float* Xb_host, float* vbs_host) {
-  GPP_REQUIRE(ctx && x0_host && v0_host && d_host && w_host && X_host && lvs_host && nll_host,
+extern "C" int gpp_gp_term_host_wait(gpp_host_ctx* ctx, int32_t ticket) {
+  GPP_REQUIRE(ctx && (ticket == 0 || ticket == 1), "gp_term_host_wait: bad ticket");
+  if (ctx->out_pending[ticket]) {
+    GPP_CUDA(cudaEventSynchronize(ctx->out_done[ticket]));
+    ctx->out_pending[ticket] = false;
+  }
+  return GPP_OK;
+}
+
+extern "C" int gpp_gp_term_host_submit(gpp_host_ctx* ctx, const float* x0_host, int64_t P, int32_t p,
+                                       const float* v0_host, int64_t nviews, int32_t q, const int64_t* d_host,
+                                       const int64_t* w_host, const float* X_host, int64_t n, int32_t L,
+                                       const float* lvs_host, float* nll_host, float* Xb_host, float* vbs_host,
+                                       int32_t* ticket) {
+  GPP_REQUIRE(ctx && x0_host && v0_host && d_host && w_host && X_host && lvs_host && nll_host && ticket,
               "gp_term_host: null pointer");
   GPP_REQUIRE(P > 0 && p > 0 && nviews > 0 && q > 0 && n > 0 && L > 0, "gp_term_host: bad shape");
   const int64_t Q64 = (int64_t)p * q;
   GPP_REQUIRE(Q64 % 4 == 0 && L % 4 == 0 && Q64 < (1 << 30), "gp_term_host: p*q and L must be multiples of 4");
   const int Q = (int)Q64;
-  cudaStream_t st = ctx->stream;
+  const bool planes = gpp_planes_supported(n, Q, L) != 0;
+  const int s = (int)(ctx->next & 1u);
+  // the results of the submission that used this slot must have been collected (its host buffers may be these again)
+  GPP_TRY(gpp_gp_term_host_wait(ctx, s));
 
-  // carve the device arena
+  // carve the device arena; X, Xb and nll are double-buffered (slot s), everything else is reused submission to submission
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -344,18 +382,36 @@ extern "C" int gpp_gp_term_host(gpp_host_ctx* ctx, const float* x0_host, int64_t
   const size_t o_v0 = take((size_t)nviews * q * 4), o_wn = take((size_t)nviews * q * 4);
   const size_t o_d = take((size_t)n * 8), o_w = take((size_t)n * 8);
   const size_t o_lvs = take(16), o_vs = take(16), o_scal = take(GPP_NSCAL * 8), o_vbs = take(16);
-  const size_t o_X = take((size_t)n * L * 4), o_Xb = take((size_t)n * L * 4), o_nll = take((size_t)n * 4);
+  size_t o_X[2], o_Xb[2], o_nll[2];
+  for (int i = 0; i < 2; ++i) {
+    o_X[i] = take((size_t)n * L * 4);
+    o_Xb[i] = take((size_t)n * L * 4);
+    o_nll[i] = take((size_t)n * 4);
+  }
   const size_t o_V = take((size_t)n * Q * 4);
   const size_t o_GC = take((size_t)Q * (Q + L) * 4), o_W = take((size_t)Q * L * 4);
-  const size_t b_gram = gpp_gram_workspace_bytes(n, Q, L), b_fac = align_up(gpp_factor_state_bytes(Q), 256) + gpp_solve_workspace_bytes(Q, L),
-               b_xb = gpp_xb_workspace_bytes(n, Q, L);
-  size_t b_ws = b_gram > b_fac ? b_gram : b_fac;
-  if (b_xb > b_ws) b_ws = b_xb;
+  const size_t o_pV = take(planes ? planes_bytes(n, Q) : 0), o_pX = take(planes ? planes_bytes(n, L) : 0);
+  // workspace: the Gram pass (or the split) first; afterwards the factor state sits at its head and the later calls use the rest
+  const size_t b_state = align_up(gpp_factor_state_bytes(Q), 256);
+  size_t b_tail = gpp_solve_workspace_bytes(Q, L), b_ws;
+  if (planes) {
+    if (pl_pass1_workspace_bytes(n, Q, L, true) > b_tail) b_tail = pl_pass1_workspace_bytes(n, Q, L, true);
+    if (pl_xb_workspace_bytes(n, Q, L) > b_tail) b_tail = pl_xb_workspace_bytes(n, Q, L);
+    b_ws = b_state + align_up(b_tail, 256);
+    if (pl_pass1_workspace_bytes(n, Q, 0, false) > b_ws) b_ws = pl_pass1_workspace_bytes(n, Q, 0, false);
+    if (split_workspace_bytes(n, Q) > b_ws) b_ws = split_workspace_bytes(n, Q);
+  } else {
+    b_ws = b_state + align_up(b_tail, 256);
+    if (gpp_gram_workspace_bytes(n, Q, L) > b_ws) b_ws = gpp_gram_workspace_bytes(n, Q, L);
+    if (gpp_xb_workspace_bytes(n, Q, L) > b_ws) b_ws = gpp_xb_workspace_bytes(n, Q, L);
+  }
   const size_t o_ws = take(b_ws);
   if (off > ctx->arena_bytes) {
+    GPP_CUDA(cudaDeviceSynchronize());
     if (ctx->arena) GPP_CUDA(cudaFree(ctx->arena));
     ctx->arena = nullptr;
     ctx->arena_bytes = 0;
+    ctx->used[0] = ctx->used[1] = false;
     GPP_CUDA(cudaMalloc(&ctx->arena, off));
     ctx->arena_bytes = off;
   }
@@ -364,27 +420,71 @@ extern "C" int gpp_gp_term_host(gpp_host_ctx* ctx, const float* x0_host, int64_t
   int64_t* d_dev = reinterpret_cast<int64_t*>(a + o_d);
   int64_t* w_dev = reinterpret_cast<int64_t*>(a + o_w);
   double* scal = reinterpret_cast<double*>(a + o_scal);
+  cudaStream_t st = ctx->compute;
 
+  // copy-in stream: X -> slot s, once the compute that last read this slot's X is done
+  if (ctx->used[s]) GPP_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->comp_done[s], 0));
+  GPP_CUDA(cudaMemcpyAsync(F(o_X[s]), X_host, (size_t)n * L * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+  GPP_CUDA(cudaEventRecord(ctx->in_done[s], ctx->copy_in));
+
+  // compute stream: everything that does not need X
   GPP_CUDA(cudaMemcpyAsync(F(o_x0), x0_host, (size_t)P * p * 4, cudaMemcpyHostToDevice, st));
   GPP_CUDA(cudaMemcpyAsync(F(o_v0), v0_host, (size_t)nviews * q * 4, cudaMemcpyHostToDevice, st));
   GPP_CUDA(cudaMemcpyAsync(d_dev, d_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   GPP_CUDA(cudaMemcpyAsync(w_dev, w_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   GPP_CUDA(cudaMemcpyAsync(F(o_lvs), lvs_host, 8, cudaMemcpyHostToDevice, st));
-  GPP_CUDA(cudaMemcpyAsync(F(o_X), X_host, (size_t)n * L * 4, cudaMemcpyHostToDevice, st));
-
   GPP_TRY(gpp_normalize_rows_fwd(F(o_x0), P, p, F(o_xn), st));
   GPP_TRY(gpp_normalize_rows_fwd(F(o_v0), nviews, q, F(o_wn), st));
-  GPP_TRY(gpp_khatri_rao_fwd(F(o_xn), P, p, F(o_wn), nviews, q, d_dev, w_dev, n, F(o_V), Q, st));
-  GPP_TRY(gpp_gram_vtz(F(o_V), Q, F(o_X), L, n, Q, L, F(o_GC), Q + L, a + o_ws, b_ws, st));
   softmax2_kernel<<<1, 32, 0, st>>>(F(o_lvs), F(o_vs));
   GPP_LAUNCH_CHECK();
-  GPP_TRY(gpp_factor_solve(F(o_GC), Q + L, Q, L, F(o_vs), n, 0, F(o_W), L, nullptr, scal, a + o_ws, b_ws, st));
-  GPP_TRY(gpp_xb_nll(F(o_V), Q, F(o_X), L, F(o_W), L, n, Q, L, scal, F(o_Xb), L, F(o_nll), a + o_ws, b_ws, st));
+  if (planes) {
+    GPP_TRY(gpp_khatri_rao_fwd_planes(F(o_xn), P, p, F(o_wn), nviews, q, d_dev, w_dev, n, F(o_V), Q, a + o_pV,
+                                      planes_bytes(n, Q), a + o_ws, b_ws, st));
+    // Gram tiles alone (L = 0), then the Cholesky: X is still in flight
+    GPP_TRY(gpp_gram_vtz_planes(a + o_pV, nullptr, n, Q, 0, 1, F(o_GC), Q + L, a + o_ws, b_ws, st));
+    GPP_TRY(gpp_factor(F(o_GC), Q + L, Q, F(o_vs), 0, nullptr, scal, a + o_ws, b_state, st));
+    GPP_CUDA(cudaStreamWaitEvent(st, ctx->in_done[s], 0));
+    // the factor state occupies the head of the workspace: the rest serves the calls below
+    char* ws2 = a + o_ws + b_state;
+    const size_t ws2_bytes = b_ws - b_state;
+    GPP_TRY(gpp_split_planes(F(o_X[s]), L, n, L, 0, a + o_pX, planes_bytes(n, L), nullptr, 0, st));
+    GPP_TRY(gpp_atb_planes(a + o_pV, a + o_pX, n, Q, L, F(o_GC) + Q, Q + L, ws2, ws2_bytes, st));
+    GPP_TRY(gpp_solve_w(F(o_GC) + Q, Q + L, Q, L, L, n, F(o_W), L, scal, a + o_ws, b_state, ws2, ws2_bytes, st));
+    if (ctx->used[s]) GPP_CUDA(cudaStreamWaitEvent(st, ctx->out_done[s], 0));   // Xb / nll of slot s have left the device
+    GPP_TRY(gpp_xb_nll_planes(a + o_pV, F(o_X[s]), L, F(o_W), L, n, Q, L, scal, F(o_Xb[s]), L, F(o_nll[s]), ws2, ws2_bytes,
+                              st));
+  } else {
+    GPP_TRY(gpp_khatri_rao_fwd(F(o_xn), P, p, F(o_wn), nviews, q, d_dev, w_dev, n, F(o_V), Q, st));
+    GPP_CUDA(cudaStreamWaitEvent(st, ctx->in_done[s], 0));
+    GPP_TRY(gpp_gram_vtz(F(o_V), Q, F(o_X[s]), L, n, Q, L, F(o_GC), Q + L, a + o_ws, b_ws, st));
+    GPP_TRY(gpp_factor_solve(F(o_GC), Q + L, Q, L, F(o_vs), n, 0, F(o_W), L, nullptr, scal, a + o_ws, b_ws, st));
+    // (gpp_factor_solve keeps the factor state at the head of the workspace; pass 2 below must not overwrite it only if a
+    //  later call needed it -- none does)
+    if (ctx->used[s]) GPP_CUDA(cudaStreamWaitEvent(st, ctx->out_done[s], 0));
+    GPP_TRY(gpp_xb_nll(F(o_V), Q, F(o_X[s]), L, F(o_W), L, n, Q, L, scal, F(o_Xb[s]), L, F(o_nll[s]), a + o_ws, b_ws, st));
+  }
   GPP_TRY(gpp_vbs(scal, n, Q, L, F(o_vbs), st));
-
-  GPP_CUDA(cudaMemcpyAsync(nll_host, F(o_nll), (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  if (Xb_host) GPP_CUDA(cudaMemcpyAsync(Xb_host, F(o_Xb), (size_t)n * L * 4, cudaMemcpyDeviceToHost, st));
   if (vbs_host) GPP_CUDA(cudaMemcpyAsync(vbs_host, F(o_vbs), 8, cudaMemcpyDeviceToHost, st));
-  GPP_CUDA(cudaStreamSynchronize(st));
+  GPP_CUDA(cudaEventRecord(ctx->comp_done[s], st));
+
+  // copy-out stream: behind this submission's compute, beside the next one's
+  GPP_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->comp_done[s], 0));
+  GPP_CUDA(cudaMemcpyAsync(nll_host, F(o_nll[s]), (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+  if (Xb_host) GPP_CUDA(cudaMemcpyAsync(Xb_host, F(o_Xb[s]), (size_t)n * L * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+  GPP_CUDA(cudaEventRecord(ctx->out_done[s], ctx->copy_out));
+  ctx->out_pending[s] = true;
+  ctx->used[s] = true;
+  *ticket = s;
+  ++ctx->next;
   return GPP_OK;
+}
+
+extern "C" int gpp_gp_term_host(gpp_host_ctx* ctx, const float* x0_host, int64_t P, int32_t p, const float* v0_host,
+                                int64_t nviews, int32_t q, const int64_t* d_host, const int64_t* w_host,
+                                const float* X_host, int64_t n, int32_t L, const float* lvs_host, float* nll_host,
+                                float* Xb_host, float* vbs_host) {
+  int32_t ticket = 0;
+  GPP_TRY(gpp_gp_term_host_submit(ctx, x0_host, P, p, v0_host, nviews, q, d_host, w_host, X_host, n, L, lvs_host,
+                                  nll_host, Xb_host, vbs_host, &ticket));
+  return gpp_gp_term_host_wait(ctx, ticket);
 }

@@ -232,12 +232,24 @@ int gpp_taylor_expansion_bwd(const float* gout, const float* Xb, int64_t ldxb, c
 /* ---------------- host-buffer entry (end-to-end measurement; train_gppvae.py:161-167) ---------------- */
 
 /* One evaluation of the GP term from HOST buffers: copies x0, v0, d, w, X, lvs to the device, builds V
- * (vmod.py:22-35), runs pass 1 / factor / pass 2 (gp.py:55-60,84-87), copies nll (n), Xb (n x L) and
- * vbs[2] back, and synchronises.  Device buffers live in the context and are reused across calls.
- * Xb_host or vbs_host may be NULL to skip that copy. Host buffers should be pinned for full PCIe speed. */
+ * (vmod.py:22-35), runs pass 1 / factor / pass 2 (gp.py:55-60,84-87) and copies nll (n), Xb (n x L) and vbs[2] back.
+ * The copy of X runs on its own stream beside the work that does not need it (the Khatri-Rao map, the Gram tiles of
+ * pass 1, the Cholesky), and the results leave on a third stream beside the compute of the NEXT submission:
+ *   gpp_gp_term_host_submit  enqueues one evaluation and returns a ticket (0 or 1: two sets of host-facing device
+ *                            buffers); at most two submissions are in flight -- a third first waits for the oldest;
+ *   gpp_gp_term_host_wait    blocks until the results of that ticket are in the host buffers;
+ *   gpp_gp_term_host         = submit + wait (synchronous).
+ * The host buffers of a submission must stay valid and untouched until its wait returns.  Device buffers live in the
+ * context and are reused across calls.  Xb_host or vbs_host may be NULL to skip that copy.  Host buffers should be
+ * pinned (page-locked) for the copies to be asynchronous and at full PCIe speed. */
 typedef struct gpp_host_ctx gpp_host_ctx;
 int gpp_host_ctx_create(gpp_host_ctx** ctx);
 int gpp_host_ctx_destroy(gpp_host_ctx* ctx);
+int gpp_gp_term_host_submit(gpp_host_ctx* ctx, const float* x0_host, int64_t P, int32_t p, const float* v0_host,
+                            int64_t nviews, int32_t q, const int64_t* d_host, const int64_t* w_host,
+                            const float* X_host, int64_t n, int32_t L, const float* lvs_host, float* nll_host,
+                            float* Xb_host, float* vbs_host, int32_t* ticket);
+int gpp_gp_term_host_wait(gpp_host_ctx* ctx, int32_t ticket);
 int gpp_gp_term_host(gpp_host_ctx* ctx, const float* x0_host, int64_t P, int32_t p, const float* v0_host,
                      int64_t nviews, int32_t q, const int64_t* d_host, const int64_t* w_host,
                      const float* X_host, int64_t n, int32_t L, const float* lvs_host, float* nll_host,

@@ -349,29 +349,53 @@ def test_full_size_c2_properties(dev):
     assert rel_err(Xb[idx].cpu(), ref.cpu()) < 1e-5
 
 
-def test_host_entry_matches_oracle(dev):
-    """gpp_gp_term_host (the end-to-end C entry bench.py times) against the oracle."""
+@pytest.mark.parametrize("n,p,q,L", [(3000, 16, 8, 64), (300, 8, 4, 32)])
+def test_host_entry_matches_oracle(dev, n, p, q, L):
+    """gpp_gp_term_host (the end-to-end C entry bench.py times) against the oracle: the synchronous call, then the
+    pipelined submit / wait form with three submissions in flight over its two buffer sets (different X per submission,
+    so a mixed-up slot would show).  The second shape is below the tensor-core tile (fp32 engine inside the entry)."""
     import ctypes
     from gppvae_b200 import _lib
     from gppvae_b200.synth import make_problem
     from oracle import gp_oracle as O
-    pr = make_problem(3000, 16, 8, 64, kind="trained", lvs=(0.3, -0.3), seed=3)
+    pr = make_problem(n, p, q, L, kind="trained", lvs=(0.3, -0.3), seed=3)
     V64 = O.feature_map(pr.x0.double(), pr.v0.double(), pr.d, pr.w)
-    o64 = O.taylor_coeff(pr.Z.double(), [V64], pr.lvs.double())
     lib = _lib.load()
     ctx = ctypes.c_void_p()
     assert lib.gpp_host_ctx_create(ctypes.byref(ctx)) == 0
-    n, L = pr.Z.shape
-    nll = torch.empty(n).pin_memory(); Xb = torch.empty(n, L).pin_memory(); vbs = torch.empty(2).pin_memory()
-    x0, v0, d, w, Z, lvs = (t.contiguous().pin_memory() for t in (pr.x0, pr.v0, pr.d, pr.w, pr.Z, pr.lvs))
-    for _ in range(2):   # second call reuses the context's device arena
-        rc = lib.gpp_gp_term_host(ctx, x0.data_ptr(), x0.shape[0], 16, v0.data_ptr(), 8, 8, d.data_ptr(), w.data_ptr(),
-                                  Z.data_ptr(), n, L, lvs.data_ptr(), nll.data_ptr(), Xb.data_ptr(), vbs.data_ptr())
-        assert rc == 0, lib.gpp_last_error()
-    assert lib.gpp_host_ctx_destroy(ctx) == 0
+    x0, v0, d, w, lvs = (t.contiguous().pin_memory() for t in (pr.x0, pr.v0, pr.d, pr.w, pr.lvs))
+    Zs = [(pr.Z * s).contiguous().pin_memory() for s in (1.0, 0.5, -2.0)]
+    outs = [(torch.empty(n).pin_memory(), torch.empty(n, L).pin_memory(), torch.empty(2).pin_memory()) for _ in Zs]
+
+    def args(i):
+        nll, Xb, vbs = outs[i]
+        return (ctx, x0.data_ptr(), x0.shape[0], p, v0.data_ptr(), q, q, d.data_ptr(), w.data_ptr(), Zs[i].data_ptr(), n, L,
+                lvs.data_ptr(), nll.data_ptr(), Xb.data_ptr(), vbs.data_ptr())
+
+    for _ in range(2):   # synchronous form; the second call reuses the context's device arena
+        assert lib.gpp_gp_term_host(*args(0)) == 0, lib.gpp_last_error()
+    o64 = O.taylor_coeff(pr.Z.double(), [V64], pr.lvs.double())
+    nll, Xb, vbs = outs[0]
     assert abs(nll.double().sum().item() - o64[3].sum().item()) / abs(o64[3].sum().item()) < NLL_TOL
     assert rel_err(Xb, o64[0]) < GRAD_TOL
     assert rel_err(vbs, o64[2]) < 1e-3
+    for t in outs:
+        for b in t:
+            b.zero_()
+    tickets = []
+    for i in range(3):   # the third submit has to wait for the first one's results internally
+        tk = ctypes.c_int32(-1)
+        assert lib.gpp_gp_term_host_submit(*args(i), ctypes.byref(tk)) == 0, lib.gpp_last_error()
+        tickets.append(tk.value)
+    assert tickets == [tickets[0], 1 - tickets[0], tickets[0]]
+    for tk in (tickets[1], tickets[2]):
+        assert lib.gpp_gp_term_host_wait(ctx, tk) == 0
+    assert lib.gpp_host_ctx_destroy(ctx) == 0
+    for i, sc in enumerate((1.0, 0.5, -2.0)):
+        oi = O.taylor_coeff(pr.Z.double() * sc, [V64], pr.lvs.double())
+        nll, Xb, vbs = outs[i]
+        assert abs(nll.double().sum().item() - oi[3].sum().item()) / abs(oi[3].sum().item()) < NLL_TOL
+        assert rel_err(Xb, oi[0]) < GRAD_TOL
 
 
 @pytest.mark.parametrize("n,Q,L", [(5000, 128, 64), (4096, 256, 256), (7777, 384, 100), (20000, 1024, 256)])
