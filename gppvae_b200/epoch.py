@@ -7,8 +7,9 @@ flags as dominating the epoch once the GP term is fast:
   * `Eps` is drawn on the device (the reference draws it on the CPU and copies it, :157);
   * per-minibatch metrics stay on the device and are read once per epoch (the reference syncs three times per
     minibatch, :304-306);
-  * `Vt` can be kept in factored form (`Vmodel.lazy`), and the factorisation built by the evaluation
-    step is reused by `taylor_coeff` (:235 and :166 factor the same (Vt, vs));
+  * `Vt` can be kept in factored form (`Vmodel.lazy`); build it ONCE per epoch with `make_vt` and pass it to
+    both `eval_step` and `train_epoch` (`Vt=`): the factorisation the evaluation step builds (:235) is then the one
+    `taylor_coeff` finds in the cache (:166 factors the same (Vt, vs)) -- two separately built objects never match;
   * rows (images) shard over ranks: every rank encodes / decodes its own images, the GP term all-reduces its small
     Q-space partials (`GP.shard_rows`), gradients are all-reduced once per epoch, before the single optimiser step.
 
@@ -42,6 +43,13 @@ def make_batches(n: int, bs: int, device, generator: Optional[torch.Generator] =
     return [perm[a:a + bs] for a in range(0, n, bs)]
 
 
+def make_vt(vm, D: torch.Tensor, W: torch.Tensor, lazy: bool = True):
+    """`Vt = vm(Dt, Wt).detach()` of train_gppvae.py:161, dense or in factored form; hand the SAME object to eval_step and
+    train_epoch so that the second use finds the first one's factorisation."""
+    with torch.no_grad():
+        return vm.lazy(D, W) if lazy else vm(D, W).detach()
+
+
 def _all_reduce_grads(params: Iterable[torch.nn.Parameter], group) -> None:
     import torch.distributed as dist
     for prm in params:
@@ -52,12 +60,13 @@ def _all_reduce_grads(params: Iterable[torch.nn.Parameter], group) -> None:
 def train_epoch(vae, vm, gp, Y: torch.Tensor, D: torch.Tensor, W: torch.Tensor, vae_optimizer, gp_optimizer, bs: int = 64,
                 eps: Optional[torch.Tensor] = None, batches: Optional[Sequence[torch.Tensor]] = None, lazy: bool = True,
                 n_total: Optional[int] = None, group=None, generator: Optional[torch.Generator] = None,
-                step: bool = True, profile: Optional[dict] = None) -> Dict[str, float]:
+                step: bool = True, profile: Optional[dict] = None, Vt=None) -> Dict[str, float]:
     """Steps 1, 2, 4, 5 of the epoch (train_gppvae.py:153-186); step 3 is `eval_step` below.
 
     Y (n x C x H x W; device or pinned host memory), D / W (n,) int64 on the device are THIS rank's rows; `n_total`
-    is the number of rows over all ranks (default: n) and `group` the process group when rows are sharded (`gp` must
-    have been given the same group with `shard_rows`).  Returns the epoch's metrics as Python floats (one sync).
+    is the number of rows over all ranks (default: n) and `group` the process group when rows are sharded (the GP is
+    told both here: `gp.shard_rows(group, n_total=n_total)`).  `Vt`: the epoch's `make_vt(...)` when `eval_step` already
+    used it.  Returns the epoch's metrics as Python floats (one sync).
     `profile`, when a dict, receives the device time of the phases in ms (encode, gp_term, minibatches, update)."""
     device = D.device
     marks = []
@@ -72,6 +81,8 @@ def train_epoch(vae, vm, gp, Y: torch.Tensor, D: torch.Tensor, W: torch.Tensor, 
     n = Y.shape[0]
     n_total = n if n_total is None else n_total
     K = float(vae.K)
+    if group is not None:
+        gp.shard_rows(group, n_total=n_total)
 
     # 1. encode, 2. sample                                                          (:154-158)
     Zm, Zs = encode_all(vae, Y, bs, device)
@@ -81,8 +92,8 @@ def train_epoch(vae, vm, gp, Y: torch.Tensor, D: torch.Tensor, W: torch.Tensor, 
     mark("encode")
 
     # 4. Taylor coefficients of the GP term over all rows                           (:161, :166-167)
-    with torch.no_grad():
-        Vt = vm.lazy(D, W) if lazy else vm(D, W).detach()
+    if Vt is None:
+        Vt = make_vt(vm, D, W, lazy)
     Zb, Vbs, vbs, gp_nll = gp.taylor_coeff(Z, [Vt])
     gp_nll_sum = gp_nll.sum()
     mark("gp_term")
@@ -108,9 +119,15 @@ def train_epoch(vae, vm, gp, Y: torch.Tensor, D: torch.Tensor, W: torch.Tensor, 
     if group is not None:
         import torch.distributed as dist
         _all_reduce_grads(list(vae.parameters()) + list(vm.parameters()) + list(gp.parameters()), group)
-        red = torch.cat([acc, gp_nll_sum.double().reshape(1)])
+        red = torch.cat([acc, gp_nll_sum.double().reshape(1),
+                         torch.tensor([float(len(batches))], device=device, dtype=torch.float64)])
         dist.all_reduce(red, group=group)
         acc, gp_nll_sum = red[:3], red[3]
+        # gp.py:131-132 adds <vbs, vs> once per MINIBATCH, so the reference's lvs gradient is ceil(N / bs) times J^T vbs
+        # (SURVEY section 9); the ranks together ran sum_r ceil(n_r / bs) minibatches, which differs whenever the shards
+        # do not divide evenly -- bring the accumulated lvs gradient back to the reference's count
+        if gp.lvs.grad is not None:
+            gp.lvs.grad.mul_(float(-(-n_total // bs)) / red[4].to(gp.lvs.grad.dtype))
     if step:
         vae_optimizer.step()
         gp_optimizer.step()
@@ -126,13 +143,14 @@ def train_epoch(vae, vm, gp, Y: torch.Tensor, D: torch.Tensor, W: torch.Tensor, 
 
 
 def eval_step(vae, vm, gp, Yv: torch.Tensor, Dv: torch.Tensor, Wv: torch.Tensor, Zm: torch.Tensor, D: torch.Tensor,
-              W: torch.Tensor, bs: int = 64, lazy: bool = True) -> Dict[str, float]:
+              W: torch.Tensor, bs: int = 64, lazy: bool = True, Vt=None) -> Dict[str, float]:
     """Out-of-sample prediction of the validation latents through the GP and the two reconstruction errors
     (train_gppvae.py:223-261): Zo = v0 Vv (Vt^T K^-1 Zm); mse_out decodes Zo, mse_val decodes the encoder's own code."""
     device = D.device
     with torch.no_grad():
         vs = gp.get_vs()
-        Vt = vm.lazy(D, W) if lazy else vm(D, W).detach()
+        if Vt is None:
+            Vt = make_vt(vm, D, W, lazy)
         U, UBi, _ = gp.U_UBi_Shb([Vt], vs)
         Kiz = gp.solve(Zm, U, UBi, vs)
         VtKiz = Vt.t().mm(Kiz)

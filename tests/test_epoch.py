@@ -146,7 +146,7 @@ def _epoch_shard_worker(rank, world, port, out):
         torch.set_num_threads(2)
         g = _golden()
         n = g["Y"].shape[0]
-        cut = (n * 3) // 5                                   # deliberately unequal shards
+        cut = int(os.environ.get("GPP_TEST_CUT", (n * 3) // 5))    # default: deliberately unequal shards
         rows = torch.arange(0, cut) if rank == 0 else torch.arange(cut, n)
         rv, grads = _cpu_epoch(g, rows, True, group=dist.group.WORLD, n_total=n)
         torch.save(dict(rv=rv, grads=grads), os.path.join(out, f"r{rank}.pt"))
@@ -169,3 +169,22 @@ def test_epoch_row_sharding_world2_gloo(tmp_path):
         _check_epoch(g, r["rv"], r["grads"])
     for name in r0["grads"]:
         assert torch.equal(r0["grads"][name], r1["grads"][name]), name
+
+
+def test_epoch_row_sharding_even_split_lvs_gradient(tmp_path, monkeypatch):
+    """20 + 20 of the 40 images with 16-image minibatches: the ranks run 2 + 2 = 4 minibatches where the reference runs
+    ceil(40 / 16) = 3, and gp.py:131-132 adds <vbs, vs> once per minibatch -- the accumulated lvs gradient has to be
+    brought back to the reference's count (it would be 4/3 of it otherwise)."""
+    import torch.multiprocessing as mp
+    g = _golden()
+    n, bs = g["Y"].shape[0], int(g["bs"])
+    assert 2 * -(-(n // 2) // bs) != -(-n // bs)            # the split really changes the minibatch count
+    monkeypatch.setenv("GPP_TEST_CUT", str(n // 2))
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_epoch_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "r0.pt"))
+    # minibatch composition differs from the reference's, so only what does not depend on it is compared: the lvs
+    # gradient (J^T vbs times the minibatch count) and the epoch metrics
+    assert rel_err(r0["grads"]["gp.lvs"], g["grad.gp.lvs"]) < 2e-3
+    for key in ("gp_nll", "pen_term"):
+        assert abs(r0["rv"][key] - float(g["out." + key])) < 2e-4 * abs(float(g["out." + key])), key
