@@ -24,6 +24,28 @@ def _guard(t: torch.Tensor):
     return torch.cuda.device(t.device)
 
 
+def _on_device(fn):
+    """Run a wrapper with the device of its first CUDA tensor argument current, and refuse operands spread over
+    several devices: the library launches on the current device and stream, whatever the pointers say."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            t = a.buf if isinstance(a, Planes) else (a.state if isinstance(a, Factorisation) else a)
+            if isinstance(t, torch.Tensor) and t.device.type == "cuda":
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    raise ValueError(f"{fn.__name__}: operands live on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -64,6 +86,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- Vmodel
+@_on_device
 def normalize_rows_fwd(x: torch.Tensor) -> torch.Tensor:
     require_cuda_f32(x, "x")
     x = x.detach().contiguous()
@@ -72,6 +95,7 @@ def normalize_rows_fwd(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+@_on_device
 def normalize_rows_bwd(x: torch.Tensor, gy: torch.Tensor) -> torch.Tensor:
     x = x.detach().contiguous()
     gy = gy.detach().contiguous()
@@ -152,6 +176,7 @@ class _PlaneRegistry:
 PLANES = _PlaneRegistry()
 
 
+@_on_device
 def split_planes(X: torch.Tensor, ldx: int, n: int, cols: int, colsq: bool = False, unit_bound: bool = False) -> Planes:
     lib = _lib.load()
     with _guard(X):
@@ -173,6 +198,7 @@ def planes_of(V: torch.Tensor, ldv: int) -> Planes:
     return pl
 
 
+@_on_device
 def khatri_rao_fwd(xn: torch.Tensor, wn: torch.Tensor, d: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """V (n x p*q) from row-normalised tables; returns a view with the reference's shape (columns are
     padded internally to a multiple of 4 when p*q is not one, by zero-padding p).  For matrices large enough for the
@@ -211,6 +237,7 @@ def khatri_rao_fwd(xn: torch.Tensor, wn: torch.Tensor, d: torch.Tensor, w: torch
     return V[:, :Q] if p_k != p else V
 
 
+@_on_device
 def khatri_rao_bwd(gV: torch.Tensor, xn: torch.Tensor, wn: torch.Tensor, d: torch.Tensor, w: torch.Tensor
                    ) -> Tuple[torch.Tensor, torch.Tensor]:
     gV = gV.detach()
@@ -227,6 +254,7 @@ def khatri_rao_bwd(gV: torch.Tensor, xn: torch.Tensor, wn: torch.Tensor, d: torc
 
 
 # ----------------------------------------------------------------------------- GP term
+@_on_device
 def gram_vtz(V: torch.Tensor, ldv: int, X: Optional[torch.Tensor], ldx: int, n: int, Q: int, L: int) -> torch.Tensor:
     """GC = V^T [V | X]  ->  (Q x (Q+L)) float32."""
     lib = _lib.load()
@@ -236,6 +264,7 @@ def gram_vtz(V: torch.Tensor, ldv: int, X: Optional[torch.Tensor], ldx: int, n: 
     return GC
 
 
+@_on_device
 def gram_vtz_planes(pV: Planes, pX: Optional[Planes], n: int, Q: int, L: int) -> torch.Tensor:
     """GC = V^T [V | X] from operand planes; the diagonal of G is V's exact column sums of squares."""
     lib = _lib.load()
@@ -248,6 +277,7 @@ def gram_vtz_planes(pV: Planes, pX: Optional[Planes], n: int, Q: int, L: int) ->
     return GC
 
 
+@_on_device
 def atb_planes(pA: Planes, pB: Planes, n: int, ka: int, kb: int) -> torch.Tensor:
     lib = _lib.load()
     dev = pA.buf.device
@@ -258,6 +288,7 @@ def atb_planes(pA: Planes, pB: Planes, n: int, ka: int, kb: int) -> torch.Tensor
     return out
 
 
+@_on_device
 def xb_nll_planes(pV: Planes, X, ldx, W, n, Q, L, scal) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     dev = X.device
@@ -270,6 +301,7 @@ def xb_nll_planes(pV: Planes, X, ldx, W, n, Q, L, scal) -> Tuple[torch.Tensor, t
     return Xb, nll
 
 
+@_on_device
 def atb(A: torch.Tensor, lda: int, B: torch.Tensor, ldb: int, n: int, ka: int, kb: int) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(ka, kb, device=A.device, dtype=torch.float32)
@@ -285,6 +317,7 @@ class Factorisation:
         self.Q, self.state, self.scal, self.Binv = Q, state, scal, Binv
 
 
+@_on_device
 def factor(G: torch.Tensor, ldg: int, Q: int, vs: torch.Tensor, want_binv: bool) -> Factorisation:
     lib = _lib.load()
     dev = G.device
@@ -297,6 +330,7 @@ def factor(G: torch.Tensor, ldg: int, Q: int, vs: torch.Tensor, want_binv: bool)
     return Factorisation(Q, state, scal, Binv)
 
 
+@_on_device
 def solve_w(f: Factorisation, C: torch.Tensor, ldc: int, L: int, L_true: int, n_total: int
             ) -> Tuple[torch.Tensor, torch.Tensor]:
     """W = (v0/vn) B^-1 C and a private copy of the scalar block extended with WNORM2 / ROWCONST."""
@@ -309,6 +343,7 @@ def solve_w(f: Factorisation, C: torch.Tensor, ldc: int, L: int, L_true: int, n_
     return W, scal
 
 
+@_on_device
 def xb_nll(V, ldv, X, ldx, W, n, Q, L, scal) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     Xb = torch.empty(n, L, device=V.device, dtype=torch.float32)
@@ -319,12 +354,14 @@ def xb_nll(V, ldv, X, ldx, W, n, Q, L, scal) -> Tuple[torch.Tensor, torch.Tensor
     return Xb, nll
 
 
+@_on_device
 def vbs_from_scal(scal: torch.Tensor, n_total: int, Q: int, L: int) -> torch.Tensor:
     out = torch.empty(2, device=scal.device, dtype=torch.float32)
     check(_lib.load().gpp_vbs(_p(scal), n_total, Q, L, _p(out), _stream()), "vbs")
     return out
 
 
+@_on_device
 def vb(V, ldv, Xb, Binv, W, scal, n, Q, L, L_true) -> torch.Tensor:
     lib = _lib.load()
     Vb = torch.empty(n, Q, device=V.device, dtype=torch.float32)
@@ -334,6 +371,7 @@ def vb(V, ldv, Xb, Binv, W, scal, n, Q, L, L_true) -> torch.Tensor:
     return Vb
 
 
+@_on_device
 def x_minus_am(X, ldx, A, lda, M, ldm, n, k, m, alpha: float) -> torch.Tensor:
     out = torch.empty(n, m, device=X.device, dtype=torch.float32)
     check(_lib.load().gpp_x_minus_am(_p(X), ldx, _p(A), lda, _p(M), ldm, n, k, m, float(alpha), _p(out), m, _stream()),
@@ -341,6 +379,7 @@ def x_minus_am(X, ldx, A, lda, M, ldm, n, k, m, alpha: float) -> torch.Tensor:
     return out
 
 
+@_on_device
 def am(A: torch.Tensor, lda: int, M: torch.Tensor, ldm: int, n: int, k: int, m: int, alpha: float = 1.0) -> torch.Tensor:
     """out = alpha * A M  (n x m)."""
     out = torch.empty(n, m, device=A.device, dtype=torch.float32)
@@ -349,6 +388,7 @@ def am(A: torch.Tensor, lda: int, M: torch.Tensor, ldm: int, n: int, k: int, m: 
 
 
 # ----------------------------------------------------------------------------- structured Khatri-Rao path
+@_on_device
 def kr_slot_sums(X: torch.Tensor, ldx: int, order: torch.Tensor, slot_start: torch.Tensor, xn: torch.Tensor,
                  nviews: int, L: int, with_x: bool) -> torch.Tensor:
     """XZ (P x nviews (p + L)) = [cnt (x) xn | per-slot sums of X]  (with_x=False: the X part alone)."""
@@ -359,6 +399,7 @@ def kr_slot_sums(X: torch.Tensor, ldx: int, order: torch.Tensor, slot_start: tor
     return XZ
 
 
+@_on_device
 def kr_assemble_gc(ST: torch.Tensor, wn: torch.Tensor, p: int, L: int, with_g: bool) -> torch.Tensor:
     nv, q = wn.shape
     Q = p * q
@@ -368,6 +409,7 @@ def kr_assemble_gc(ST: torch.Tensor, wn: torch.Tensor, p: int, L: int, with_g: b
     return GC
 
 
+@_on_device
 def kr_assemble_m(W: torch.Tensor, wn: torch.Tensor, p: int, L: int) -> torch.Tensor:
     nv, q = wn.shape
     M = torch.empty(p, nv * L, device=W.device, dtype=torch.float32)
@@ -376,6 +418,7 @@ def kr_assemble_m(W: torch.Tensor, wn: torch.Tensor, p: int, L: int) -> torch.Te
     return M
 
 
+@_on_device
 def kr_xb_nll(X: torch.Tensor, ldx: int, Y: torch.Tensor, d: torch.Tensor, w: torch.Tensor, P: int, nviews: int,
               L: int, scal: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
