@@ -66,6 +66,9 @@ _SIGNATURES = {
     "gpp_xb_planes_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "gpp_xb_nll_planes": (c_int, [_PF, _PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, _PF, _PF, c_int64, _PF,
                                   _PF, c_size_t, c_void_p]),
+    "gpp_vb_planes_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "gpp_vb_planes": (c_int, [_PF, _PF, c_int64, _PF, _PF, c_int64, _PF, c_int64, c_int32, c_int32, c_int32, _PF, c_int64,
+                              _PF, c_size_t, c_void_p]),
     "gpp_am": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, c_float, _PF, c_int64, c_void_p]),
     "gpp_kr_slot_sums": (c_int, [_PF, c_int64, _PF, _PF, _PF, c_int64, c_int32, c_int32, c_int32, c_int32, _PF, c_int64,
                                  c_void_p]),

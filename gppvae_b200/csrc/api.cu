@@ -282,6 +282,20 @@ extern "C" int gpp_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb
   return launch_vb(V, ldv, Xb, ldxb, Binv, Q, W, ldw, scal, n, Q, L, L_true, Vb, ldvb, (cudaStream_t)stream);
 }
 
+extern "C" size_t gpp_vb_planes_workspace_bytes(int64_t n, int32_t Q, int32_t L) { return pl_vb_workspace_bytes(n, Q, L); }
+
+extern "C" int gpp_vb_planes(const void* planesV, const float* Xb, int64_t ldxb, const float* Binv, const float* W,
+                             int64_t ldw, const double* scal, int64_t n, int32_t Q, int32_t L, int32_t L_true, float* Vb,
+                             int64_t ldvb, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(Q > 0 && L > 0 && Q % 4 == 0 && L % 4 == 0 && L_true > 0 && L_true <= L, "vb_planes: bad shape");
+  GPP_REQUIRE(pl_rows_supported(n, Q + L, Q) && Q >= 128, "vb_planes: shape below the tensor-core tile");
+  GPP_REQUIRE(planes_ok(planesV) && mat_ok(Xb, ldxb, L) && mat_ok(W, ldw, L) && mat_ok(Vb, ldvb, Q) && Binv &&
+                  aligned16(Binv) && scal,
+              "vb_planes: bad pointer / leading dimension");
+  return launch_pl_vb(planesV, Xb, ldxb, Binv, W, ldw, scal, n, Q, L, L_true, Vb, ldvb, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------ host-buffer entry
 namespace gpp {
 __global__ void softmax2_kernel(const float* __restrict__ lvs, float* __restrict__ vs) {

@@ -839,4 +839,51 @@ int launch_pl_xb(const void* planesV, const float* X, int64_t ldx, const float* 
   return GPP_OK;
 }
 
+// ---------------------------------------------------------------- Vb on planes
+// Vb = (v0/vn) L_true V B^-1 - Xb W^T = [V | Xb] . [ (v0/vn) L_true Binv ; -W^T ]   (gp.py:68-71)
+// The two parts of A share one accumulator, hence one scale: V's planes carry 2^(7 - eV), Xb's their own 2^(7 - eXb);
+// the difference 2^(eXb - eV) (exact) goes into the -W^T rows of the stacked right-hand side before IT is split.
+__global__ void __launch_bounds__(256) build_bstk_scaled_kernel(const float* __restrict__ Binv, const float* __restrict__ W,
+                                                                int64_t ldw, const double* __restrict__ scal, int Q, int L,
+                                                                int L_true, const uint32_t* __restrict__ metaV,
+                                                                const uint32_t* __restrict__ metaXb,
+                                                                float* __restrict__ Bstk) {
+  const float coef = (float)(scal[GPP_S_V0] / scal[GPP_S_VN] * (double)L_true);
+  const float wsc = -exp2f((float)(exp_of_bits(metaXb) - exp_of_bits(metaV)));
+  const int64_t total = (int64_t)(Q + L) * Q;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / Q), c = (int)(e - (int64_t)r * Q);
+    Bstk[e] = r < Q ? coef * Binv[(int64_t)r * Q + c] : wsc * W[(int64_t)c * ldw + (r - Q)];
+  }
+}
+
+size_t pl_vb_workspace_bytes(int64_t n, int Q, int L) {
+  return align_up(planes_bytes(n, L), 256) + align_up((size_t)(Q + L) * Q * sizeof(float), 256) +
+         align_up(planes_bytes(Q + L, Q), 256);
+}
+
+int launch_pl_vb(const void* planesV, const float* Xb, int64_t ldxb, const float* Binv, const float* W, int64_t ldw,
+                 const double* scal, int64_t n, int Q, int L, int L_true, float* Vb, int64_t ldvb, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+  const size_t need = pl_vb_workspace_bytes(n, Q, L);
+  if (!ws || ws_bytes < need) {
+    set_error("vb (planes): workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    return GPP_ERR_WORKSPACE;
+  }
+  char* wsb = static_cast<char*>(ws);
+  void* planesXb = wsb;
+  float* Bstk = reinterpret_cast<float*>(wsb + align_up(planes_bytes(n, L), 256));
+  void* planesB = wsb + align_up(planes_bytes(n, L), 256) + align_up((size_t)(Q + L) * Q * sizeof(float), 256);
+  GPP_TRY(launch_split_planes(Xb, ldxb, n, L, planesXb, nullptr, 0, false, nullptr, 0, st));
+  const PlanesView pv = planes_view(const_cast<void*>(planesV), n, Q);
+  const PlanesView px = planes_view(planesXb, n, L);
+  build_bstk_scaled_kernel<<<1024, 256, 0, st>>>(Binv, W, ldw, scal, Q, L, L_true, pv.meta, px.meta, Bstk);
+  GPP_LAUNCH_CHECK();
+  GPP_TRY(launch_split_planes(Bstk, Q, (int64_t)Q + L, Q, planesB, nullptr, 0, false, nullptr, 0, st));
+  const PlanesView pb = planes_view(planesB, (int64_t)Q + L, Q);
+  PlRowsParams p{};
+  p.mode = 1; p.out = Vb; p.ldo = ldvb; p.alpha_host = 1.f;
+  return launch_pl_rows(pv, Q, &px, L, pb, n, Q, p, st);
+}
+
 }  // namespace gpp

@@ -80,6 +80,11 @@ int launch_pl_xb(const void* planesV, const float* X, int64_t ldx, const float* 
                  double* scal, float alpha_host, float* Xb, int64_t ldxb, float* nll, void* ws, size_t ws_bytes,
                  cudaStream_t st);
 
+size_t pl_vb_workspace_bytes(int64_t n, int Q, int L);
+int launch_pl_vb(const void* planesV, const float* Xb, int64_t ldxb, const float* Binv, const float* W, int64_t ldw,
+                 const double* scal, int64_t n, int Q, int L, int L_true, float* Vb, int64_t ldvb, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
+
 bool tc_rows_supported(int64_t n, int K, int ncols);
 size_t tc_xb_workspace_bytes(int64_t n, int L);
 int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n,

@@ -392,7 +392,7 @@ class GP(nn.Module):
             Xb, nll = ops.xb_nll(Vm, ldv, Xm, ldx, W, n, Q, Lk, scal)
         self._stage("pass2:end")
         return dict(vs=vs, Vm=Vm, ldv=ldv, Q=Q, Qtrue=Qtrue, n=n, L=L, Lk=Lk, n_total=n_total, fac=fac, W=W,
-                    scal=scal, Xb=Xb, nll=nll)
+                    scal=scal, Xb=Xb, nll=nll, pV=pV)
 
     def taylor_coeff(self, X: torch.Tensor, Vs: Sequence[torch.Tensor], need_vb: bool = True
                      ) -> Tuple[torch.Tensor, List[torch.Tensor], torch.Tensor, torch.Tensor]:
@@ -408,7 +408,10 @@ class GP(nn.Module):
         if need_vb and c["Vm"] is None:
             Vbs = [LazyVb(c["kr"], c["Xb"], c["fac"], c["W"], scal, Q, Lk, L)]
         elif need_vb:
-            Vb = ops.vb(c["Vm"], c["ldv"], c["Xb"], c["fac"].Binv, c["W"], scal, c["n"], Q, Lk, L)
+            if c.get("pV") is not None:
+                Vb = ops.vb_planes(c["pV"], c["Xb"], c["fac"].Binv, c["W"], scal, c["n"], Q, Lk, L)
+            else:
+                Vb = ops.vb(c["Vm"], c["ldv"], c["Xb"], c["fac"].Binv, c["W"], scal, c["n"], Q, Lk, L)
             Vbs = [Vb[:, : c["Qtrue"]] if c["Qtrue"] != Q else Vb]
             self._stage("vb:end")
         else:

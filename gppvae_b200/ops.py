@@ -302,6 +302,16 @@ def xb_nll_planes(pV: Planes, X, ldx, W, n, Q, L, scal) -> Tuple[torch.Tensor, t
 
 
 @_on_device
+def vb_planes(pV: Planes, Xb, Binv, W, scal, n, Q, L, L_true) -> torch.Tensor:
+    lib = _lib.load()
+    Vb = torch.empty(n, Q, device=Xb.device, dtype=torch.float32)
+    ws = _workspace(lib.gpp_vb_planes_workspace_bytes(n, Q, L), Xb.device)
+    check(lib.gpp_vb_planes(pV.ptr, _p(Xb), Xb.stride(0), _p(Binv), _p(W), W.stride(0), _p(scal), n, Q, L, L_true, _p(Vb), Q,
+                            _p(ws), ws.numel(), _stream()), "vb_planes")
+    return Vb
+
+
+@_on_device
 def atb(A: torch.Tensor, lda: int, B: torch.Tensor, ldb: int, n: int, ka: int, kb: int) -> torch.Tensor:
     lib = _lib.load()
     out = torch.empty(ka, kb, device=A.device, dtype=torch.float32)

@@ -180,6 +180,11 @@ size_t gpp_xb_planes_workspace_bytes(int64_t n, int32_t Q, int32_t L);
 int gpp_xb_nll_planes(const void* planesV, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n,
                       int32_t Q, int32_t L, double* scal, float* Xb, int64_t ldxb, float* nll, void* workspace,
                       size_t workspace_bytes, gpp_stream_t stream);
+/* the contract of gpp_vb with V as planes (Xb, Binv, W stay fp32 and are split internally) */
+size_t gpp_vb_planes_workspace_bytes(int64_t n, int32_t Q, int32_t L);
+int gpp_vb_planes(const void* planesV, const float* Xb, int64_t ldxb, const float* Binv, const float* W, int64_t ldw,
+                  const double* scal, int64_t n, int32_t Q, int32_t L, int32_t L_true, float* Vb, int64_t ldvb,
+                  void* workspace, size_t workspace_bytes, gpp_stream_t stream);
 /* 1 when the planes kernels take this shape (n >= 512, Q >= 128), else the fp32 entries must be used */
 int gpp_planes_supported(int64_t n, int32_t Q, int32_t L);
 

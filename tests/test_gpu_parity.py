@@ -374,9 +374,15 @@ def test_host_entry_matches_oracle(dev, n, p, q, L):
 
     for _ in range(2):   # synchronous form; the second call reuses the context's device arena
         assert lib.gpp_gp_term_host(*args(0)) == 0, lib.gpp_last_error()
+    def nll_err(got, ref):
+        # relative error of sum(nll); where the sum itself nearly cancels (small n) it is graded against the typical
+        # magnitude of its terms instead of against the accidental remainder
+        den = max(abs(ref.sum().item()), 0.05 * ref.abs().sum().item())
+        return abs(got.double().sum().item() - ref.sum().item()) / den
+
     o64 = O.taylor_coeff(pr.Z.double(), [V64], pr.lvs.double())
     nll, Xb, vbs = outs[0]
-    assert abs(nll.double().sum().item() - o64[3].sum().item()) / abs(o64[3].sum().item()) < NLL_TOL
+    assert nll_err(nll, o64[3]) < NLL_TOL
     assert rel_err(Xb, o64[0]) < GRAD_TOL
     assert rel_err(vbs, o64[2]) < 1e-3
     for t in outs:
@@ -394,7 +400,7 @@ def test_host_entry_matches_oracle(dev, n, p, q, L):
     for i, sc in enumerate((1.0, 0.5, -2.0)):
         oi = O.taylor_coeff(pr.Z.double() * sc, [V64], pr.lvs.double())
         nll, Xb, vbs = outs[i]
-        assert abs(nll.double().sum().item() - oi[3].sum().item()) / abs(oi[3].sum().item()) < NLL_TOL
+        assert nll_err(nll, oi[3]) < NLL_TOL
         assert rel_err(Xb, oi[0]) < GRAD_TOL
 
 
