@@ -1,7 +1,10 @@
 """Run the Q-space factorisation a few times (for ncu --cache-control none timing of its kernels)."""
-import sys, time
+import os, sys, time
 import torch
 sys.path.insert(0, ".")
+if os.environ.get("GPPVAE_LIB"):
+    import gppvae_b200._lib as L
+    L.LIB_PATH = os.environ["GPPVAE_LIB"]
 from gppvae_b200 import ops
 Q = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3

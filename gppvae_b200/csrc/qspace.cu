@@ -200,186 +200,6 @@ __device__ __forceinline__ void invert64(const Block64& As, Block64& Xs, float (
   }
 }
 
-// Fused factorisation + panel solve of one step, register-tiled (round 2): the stacked 128 x 64 matrix [A11; A21] is
-// held as 4 x 4 register tiles, thread (ty, tx) owning tile (ty, tx) of BOTH blocks, and eliminated one 4-column tile
-// column at a time:
-//   the thread of diagonal tile tj factors it (4 x 4 Cholesky) and inverts the factor;
-//   the threads of tile column tj turn their tiles into L (x L4^-T) and publish them in shared memory;
-//   every tile to the right takes its rank-4 update -- and the thread of the NEXT diagonal tile factors it right away,
-//   beside the other threads' updates.
-// Two block barriers per tile column, no separate triangular solve: A21 is eliminated with A11 (chol_step_kernel spent
-// 21 k cycles in factor64 and 11 k in the substitution that followed; this routine replaces both).
-struct FusedScratch {
-  float colA[2][NB][4];   // L[row][4 tj + k] of the diagonal block for the current tile column (double-buffered)
-  float colX[2][NB][4];   // the same for this CTA's block row
-  float li4[16];          // inverse of the current 4 x 4 diagonal factor
-};
-
-__device__ __forceinline__ void chol4_and_inverse(float (&a)[4][4], float* __restrict__ li_out, float (*col_out)[4]) {
-  float rinv[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float piv = a[c][c];
-    float r = rsqrtf(piv);
-    r = r * fmaf(-0.5f * piv * r, r, 1.5f);   // one Newton step on the MUFU estimate: ~1 ulp
-    rinv[c] = r;
-    a[c][c] = piv * r;
-#pragma unroll
-    for (int rr = c + 1; rr < 4; ++rr) a[rr][c] *= r;
-#pragma unroll
-    for (int c2 = c + 1; c2 < 4; ++c2)
-#pragma unroll
-      for (int rr = c2; rr < 4; ++rr) a[rr][c2] = fmaf(-a[rr][c], a[c2][c], a[rr][c2]);
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = r + 1; c < 4; ++c) a[r][c] = 0.f;
-  float li[4][4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) li[r][c] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    li[i][i] = rinv[i];
-#pragma unroll
-    for (int j = 0; j < i; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int k = j; k < i; ++k) s = fmaf(a[i][k], li[k][j], s);
-      li[i][j] = -rinv[i] * s;
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) li_out[r * 4 + c] = li[r][c];
-    *reinterpret_cast<float4*>(col_out[r]) = make_float4(a[r][0], a[r][1], a[r][2], a[r][3]);
-  }
-}
-
-// As <- L11 (strict upper part zero), Xs <- A21 L11^-T (when has_x).  256 threads.
-__device__ __forceinline__ void factor_solve64(Block64& As, Block64& Xs, bool has_x, FusedScratch& F) {
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  float a[4][4], x[4][4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const float4 va = *reinterpret_cast<const float4*>(&As.a[4 * ty + r][4 * tx]);
-    a[r][0] = va.x; a[r][1] = va.y; a[r][2] = va.z; a[r][3] = va.w;
-    float4 vx = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_x) vx = *reinterpret_cast<const float4*>(&Xs.a[4 * ty + r][4 * tx]);
-    x[r][0] = vx.x; x[r][1] = vx.y; x[r][2] = vx.z; x[r][3] = vx.w;
-  }
-  if (ty == 0 && tx == 0) chol4_and_inverse(a, F.li4, &F.colA[0][0]);
-  __syncthreads();
-  for (int tj = 0; tj < NB / 4; ++tj) {
-    const int buf = tj & 1;
-    if (tx == tj) {
-      // tiles of tile column tj become L: t <- t Li^T, i.e. t[r][c] = sum_{k <= c} t[r][k] Li[c][k]
-      float li[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float4 v = *reinterpret_cast<const float4*>(&F.li4[4 * r]);
-        li[r][0] = v.x; li[r][1] = v.y; li[r][2] = v.z; li[r][3] = v.w;
-      }
-      if (ty > tj) {
-        float t[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float sacc = 0.f;
-#pragma unroll
-            for (int k = 0; k <= c; ++k) sacc = fmaf(a[r][k], li[c][k], sacc);
-            t[r][c] = sacc;
-          }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) a[r][c] = t[r][c];
-          *reinterpret_cast<float4*>(F.colA[buf][4 * ty + r]) = make_float4(t[r][0], t[r][1], t[r][2], t[r][3]);
-        }
-      } else if (ty < tj) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) a[r][c] = 0.f;   // strict upper part of the factor
-      }
-      if (has_x) {
-        float t[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float sacc = 0.f;
-#pragma unroll
-            for (int k = 0; k <= c; ++k) sacc = fmaf(x[r][k], li[c][k], sacc);
-            t[r][c] = sacc;
-          }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) x[r][c] = t[r][c];
-          *reinterpret_cast<float4*>(F.colX[buf][4 * ty + r]) = make_float4(t[r][0], t[r][1], t[r][2], t[r][3]);
-        }
-      }
-    }
-    __syncthreads();
-    if (tx > tj) {
-      float lc[4][4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(F.colA[buf][4 * tx + c]);
-        lc[c][0] = v.x; lc[c][1] = v.y; lc[c][2] = v.z; lc[c][3] = v.w;
-      }
-      if (ty >= tx) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float4 v = *reinterpret_cast<const float4*>(F.colA[buf][4 * ty + r]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float t = a[r][c];
-            t = fmaf(-v.x, lc[c][0], t); t = fmaf(-v.y, lc[c][1], t);
-            t = fmaf(-v.z, lc[c][2], t); t = fmaf(-v.w, lc[c][3], t);
-            a[r][c] = t;
-          }
-        }
-        // the next diagonal tile is complete now: factor it beside the other threads' updates
-        if (ty == tj + 1 && tx == tj + 1) chol4_and_inverse(a, F.li4, &F.colA[buf ^ 1][4 * (tj + 1)]);
-      }
-      if (has_x) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float4 v = *reinterpret_cast<const float4*>(F.colX[buf][4 * ty + r]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float t = x[r][c];
-            t = fmaf(-v.x, lc[c][0], t); t = fmaf(-v.y, lc[c][1], t);
-            t = fmaf(-v.z, lc[c][2], t); t = fmaf(-v.w, lc[c][3], t);
-            x[r][c] = t;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    if (tx > ty) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) a[r][c] = 0.f;
-    }
-    *reinterpret_cast<float4*>(&As.a[4 * ty + r][4 * tx]) = make_float4(a[r][0], a[r][1], a[r][2], a[r][3]);
-    if (has_x) *reinterpret_cast<float4*>(&Xs.a[4 * ty + r][4 * tx]) = make_float4(x[r][0], x[r][1], x[r][2], x[r][3]);
-  }
-  __syncthreads();
-}
-
-#ifndef GPP_CHOL_FUSED
-#define GPP_CHOL_FUSED 1
-#endif
-
 // One step of the blocked Cholesky with look-ahead, ONE kernel per 64-wide panel j:
 //   panel CTAs (blockIdx < nb - j; CTA 0 = the diagonal block only, CTA b >= 1 = block row j + b):
 //       apply the rank-64 update of panel j-1 to their own 64 x 64 blocks of column j (the diagonal block redundantly
@@ -403,7 +223,6 @@ struct StepSmem {
   Block64 As, Xs, LsT, PsT;   // diagonal block, this CTA's block row, L[j, j-1]^T, L[j+b, j-1]^T
   float rd16[SB];
   float li16[NB / SB][SB][SB + 1];
-  FusedScratch fused;
 };
 constexpr size_t kStepSmemBytes = sizeof(StepSmem) > sizeof(TileSmem) ? sizeof(StepSmem) : sizeof(TileSmem);
 
@@ -546,15 +365,6 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
   }
   __syncthreads();
   CPROF(2);
-#if GPP_CHOL_FUSED
-  factor_solve64(S.As, S.Xs, b > 0, S.fused);
-  CPROF(3);
-  if (b == 0) {
-    float* dst = Ld + (size_t)j * NB * NB;
-    for (int e = tid; e < NB * NB; e += kPotfThreads) dst[e] = S.As.a[e >> 6][e & 63];
-    return;
-  }
-#else
   factor64(S.As, S.rd16, S.li16);
   CPROF(3);
   if (b == 0) {
@@ -597,7 +407,6 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
       __syncwarp();
     }
   }
-#endif
   __syncthreads();
   CPROF(4);
   for (int e = tid; e < NB * NB; e += kPotfThreads) P[(int64_t)(e >> 6) * Qp + (e & 63)] = S.Xs.a[e >> 6][e & 63];
