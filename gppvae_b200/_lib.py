@@ -48,8 +48,9 @@ _SIGNATURES = {
     "gpp_vb_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "gpp_vb": (c_int, [_PF, c_int64, _PF, c_int64, _PF, _PF, c_int64, _PF, c_int64, c_int32, c_int32, c_int32, _PF,
                        c_int64, _PF, c_size_t, c_void_p]),
+    "gpp_rows_workspace_bytes": (c_size_t, []),
     "gpp_x_minus_am": (c_int, [_PF, c_int64, _PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, c_float, _PF,
-                               c_int64, c_void_p]),
+                               c_int64, _PF, c_size_t, c_void_p]),
     "gpp_atb_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "gpp_atb": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, _PF, c_int64, _PF, c_size_t,
                         c_void_p]),
@@ -69,7 +70,8 @@ _SIGNATURES = {
     "gpp_vb_planes_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "gpp_vb_planes": (c_int, [_PF, _PF, c_int64, _PF, _PF, c_int64, _PF, c_int64, c_int32, c_int32, c_int32, _PF, c_int64,
                               _PF, c_size_t, c_void_p]),
-    "gpp_am": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, c_float, _PF, c_int64, c_void_p]),
+    "gpp_am": (c_int, [_PF, c_int64, _PF, c_int64, c_int64, c_int32, c_int32, c_float, _PF, c_int64, _PF, c_size_t,
+                       c_void_p]),
     "gpp_kr_slot_sums": (c_int, [_PF, c_int64, _PF, _PF, _PF, c_int64, c_int32, c_int32, c_int32, c_int32, _PF, c_int64,
                                  c_void_p]),
     "gpp_kr_assemble_gc": (c_int, [_PF, c_int64, _PF, c_int32, c_int32, c_int32, c_int32, c_int32, _PF, c_int64,

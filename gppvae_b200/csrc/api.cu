@@ -230,28 +230,43 @@ extern "C" int gpp_xb_nll(const float* V, int64_t ldv, const float* X, int64_t l
                    (cudaStream_t)stream);
 }
 
+// 256 bytes: the device slots that receive the operands' exact maxima (scales of the fp16 operands)
+extern "C" size_t gpp_rows_workspace_bytes(void) { return 256; }
+
 extern "C" int gpp_x_minus_am(const float* X, int64_t ldx, const float* A, int64_t lda, const float* M, int64_t ldm,
-                              int64_t n, int32_t k, int32_t m, float alpha, float* out, int64_t ldo,
-                              gpp_stream_t stream) {
+                              int64_t n, int32_t k, int32_t m, float alpha, float* out, int64_t ldo, void* workspace,
+                              size_t workspace_bytes, gpp_stream_t stream) {
   GPP_REQUIRE(n >= 0 && k > 0 && m > 0 && k % 4 == 0 && m % 4 == 0, "x_minus_am: bad shape");
   GPP_REQUIRE(mat_ok(X, ldx, m) && mat_ok(A, lda, k) && mat_ok(M, ldm, m) && mat_ok(out, ldo, m),
               "x_minus_am: bad pointer / leading dimension");
-  if (tc_rows_supported(n, k, m))
-    return launch_tc_xb(A, lda, X, ldx, M, ldm, n, k, m, nullptr, alpha, out, ldo, nullptr, nullptr, 0,
+  if (tc_rows_supported(n, k, m)) {
+    if (!workspace || workspace_bytes < 256 || !aligned16(workspace)) {
+      set_error("x_minus_am: workspace of gpp_rows_workspace_bytes() required (%zu bytes given)", workspace_bytes);
+      return GPP_ERR_WORKSPACE;
+    }
+    return launch_tc_xb(A, lda, X, ldx, M, ldm, n, k, m, nullptr, alpha, out, ldo, nullptr, workspace, workspace_bytes,
                         (cudaStream_t)stream);
+  }
   return launch_xb(A, lda, X, ldx, M, ldm, n, k, m, nullptr, alpha, out, ldo, nullptr, nullptr, 0,
                    (cudaStream_t)stream);
 }
 
 extern "C" int gpp_am(const float* A, int64_t lda, const float* M, int64_t ldm, int64_t n, int32_t k, int32_t m,
-                      float alpha, float* out, int64_t ldo, gpp_stream_t stream) {
+                      float alpha, float* out, int64_t ldo, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
   GPP_REQUIRE(n >= 0 && k > 0 && m > 0 && k % 4 == 0 && m % 4 == 0 && n < (1ll << 31), "am: bad shape");
   GPP_REQUIRE(mat_ok(A, lda, k) && mat_ok(M, ldm, m) && mat_ok(out, ldo, m), "am: bad pointer / leading dimension");
   if (n == 0) return GPP_OK;
   if (tc_blockgemm_supported((int)n, k, m)) {
+    if (!workspace || workspace_bytes < 256 || !aligned16(workspace)) {
+      set_error("am: workspace of gpp_rows_workspace_bytes() required (%zu bytes given)", workspace_bytes);
+      return GPP_ERR_WORKSPACE;
+    }
+    uint32_t* amax = static_cast<uint32_t*>(workspace);
+    GPP_TRY(tc_absmax(A, lda, n, k, amax, (cudaStream_t)stream));
+    GPP_TRY(tc_absmax(M, ldm, k, m, amax + 1, (cudaStream_t)stream));
     TcBlockGemm g{};
     g.n = (int)n; g.n_last = (int)n; g.K = k; g.ncols = m; g.batches = 1; g.alpha = alpha;
-    return launch_tc_blockgemm(A, n, k, lda, M, k, m, ldm, out, ldo, g, nullptr, (cudaStream_t)stream);
+    return launch_tc_blockgemm(A, n, k, lda, M, k, m, ldm, out, ldo, g, amax, (cudaStream_t)stream);
   }
   GemmParams g{};
   g.A = A; g.lda = lda; g.B = M; g.ldb = ldm; g.C = out; g.ldc = ldo;

@@ -1129,9 +1129,13 @@ int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const
     p.quad_part = static_cast<float*>(ws);
     p.xb2_part = reinterpret_cast<double*>(static_cast<char*>(ws) + align_up((size_t)col_tiles * 2 * n * sizeof(float), 256));
   }
+  // exact operand maxima (fp16 scales): the last 256 bytes of the NLL workspace, or the whole 256-byte workspace of the
+  // generic X - A M form
   uint32_t* amax = nullptr;
   if (nll)
     amax = reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + tc_xb_workspace_bytes(n, L) - 256);
+  else if (ws && ws_bytes >= 256)
+    amax = static_cast<uint32_t*>(ws);
   GPP_TRY(launch_rows(V, ldv, Q, nullptr, 0, 0, W, ldw, n, L, p, amax, st));
   if (nll) {
     double* fin = p.xb2_part + align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256) / sizeof(double);

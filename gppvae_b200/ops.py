@@ -384,8 +384,9 @@ def vb(V, ldv, Xb, Binv, W, scal, n, Q, L, L_true) -> torch.Tensor:
 @_on_device
 def x_minus_am(X, ldx, A, lda, M, ldm, n, k, m, alpha: float) -> torch.Tensor:
     out = torch.empty(n, m, device=X.device, dtype=torch.float32)
-    check(_lib.load().gpp_x_minus_am(_p(X), ldx, _p(A), lda, _p(M), ldm, n, k, m, float(alpha), _p(out), m, _stream()),
-          "x_minus_am")
+    ws = _workspace(256, X.device)
+    check(_lib.load().gpp_x_minus_am(_p(X), ldx, _p(A), lda, _p(M), ldm, n, k, m, float(alpha), _p(out), m, _p(ws),
+                                     ws.numel(), _stream()), "x_minus_am")
     return out
 
 
@@ -393,7 +394,8 @@ def x_minus_am(X, ldx, A, lda, M, ldm, n, k, m, alpha: float) -> torch.Tensor:
 def am(A: torch.Tensor, lda: int, M: torch.Tensor, ldm: int, n: int, k: int, m: int, alpha: float = 1.0) -> torch.Tensor:
     """out = alpha * A M  (n x m)."""
     out = torch.empty(n, m, device=A.device, dtype=torch.float32)
-    check(_lib.load().gpp_am(_p(A), lda, _p(M), ldm, n, k, m, float(alpha), _p(out), m, _stream()), "am")
+    ws = _workspace(256, A.device)
+    check(_lib.load().gpp_am(_p(A), lda, _p(M), ldm, n, k, m, float(alpha), _p(out), m, _p(ws), ws.numel(), _stream()), "am")
     return out
 
 

@@ -145,8 +145,12 @@ int gpp_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb, const flo
 
 /* out = alpha * (X - A M)   X:(n x m) A:(n x k) M:(k x m).  The generic form of gp.py:42-44 used by
  * GP.solve() when the caller hands in dense U / UBi tensors.  alpha is a host scalar. */
+/* (workspace: gpp_rows_workspace_bytes() bytes, 16-byte aligned -- it receives the operands' exact maxima, from which
+ * the fp16 operand scales of the tensor-core form are derived; may be NULL below the tensor-core tile) */
+size_t gpp_rows_workspace_bytes(void);
 int gpp_x_minus_am(const float* X, int64_t ldx, const float* A, int64_t lda, const float* M, int64_t ldm,
-                   int64_t n, int32_t k, int32_t m, float alpha, float* out, int64_t ldo, gpp_stream_t stream);
+                   int64_t n, int32_t k, int32_t m, float alpha, float* out, int64_t ldo, void* workspace,
+                   size_t workspace_bytes, gpp_stream_t stream);
 /* ---------------- pre-split operand planes (the fast form of the two N-long sweeps) ----------------
  * The tensor cores take fp16 operands; an fp32-accurate product needs every operand as hi + lo (hi = the value rounded
  * to 11 significant bits, lo = the remainder, one power-of-two scale per matrix).  A `planes` buffer holds that form
@@ -195,7 +199,7 @@ int gpp_atb(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n,
 
 /* out = alpha * A M   A:(n x k) M:(k x m).  (Y = xn [M_0 | M_1 | ...] of the structured path below.) */
 int gpp_am(const float* A, int64_t lda, const float* M, int64_t ldm, int64_t n, int32_t k, int32_t m, float alpha,
-           float* out, int64_t ldo, gpp_stream_t stream);
+           float* out, int64_t ldo, void* workspace, size_t workspace_bytes, gpp_stream_t stream);
 
 /* ---------------- structured Khatri-Rao path (V never materialised) ----------------
  * V[i, j q + k] = xn[d_i, j] wn[w_i, k] (vmod.py:28-35), so V^T V, V^T X and V W (gp.py:30,42-44) factor through the
