@@ -232,10 +232,16 @@ constexpr int kOuterCholMinQ = 6144;   // padded Q from which the Cholesky uses 
 // whose columns received everything from the tensor-core update of the previous outer block).  wide_cols < 0: the wide
 // role covers the whole trailing matrix; otherwise only its first wide_cols (<= 2) 64-column blocks, all rows -- the
 // columns of the current 256-wide outer block; the rest of the matrix gets the whole outer block in one rank-256 update.
-// Trailing update of panel j - 1 on ONE 128 x 128 tile (index widx of the lower-triangular tile list, or of the tile
-// column list when wide_cols >= 0): A[i, c] -= L[i, j-1] L[c, j-1]^T.
-__device__ __forceinline__ void chol_wide_tile(float* __restrict__ Bm, int Qp, int k0, int wide_cols, int widx,
-                                               TileSmem& sm) {
+__global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __restrict__ Bm, int Qp, int j,
+                                                                 float* __restrict__ Ld, int apply_prev, int wide_cols) {
+  extern __shared__ __align__(16) uint8_t step_smem[];
+  const int tid = threadIdx.x;
+  const int nb = Qp / NB, k0 = j * NB;
+  const int npanel = nb - j;
+  if ((int)blockIdx.x >= npanel) {
+    // ------------------------------------------------------------ wide role: trailing update of panel j - 1
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(step_smem);
+    const int widx = (int)blockIdx.x - npanel;
     int ti, tc;
     if (wide_cols < 0) {
       ti = (int)((sqrtf(8.f * (float)widx + 1.f) - 1.f) * 0.5f);
@@ -273,36 +279,6 @@ __device__ __forceinline__ void chol_wide_tile(float* __restrict__ Bm, int Qp, i
         *c4 = v;
       }
     }
-    }
-
-// The wide role as a queue: every CTA that has nothing (else) to do takes the next tile of this step's trailing update
-// from a device counter -- the wide CTAs from the start, the panel CTAs once their panel work is stored.  (Round 1
-// launched one CTA per tile: 496 tiles on the 296 - 63 slots the panel CTAs leave are three rounds of ~15 us where 2.1
-// would do, and the 63 slots stayed idle after the 22 us of panel work.)  Which CTA updates a tile does not change
-// the result.
-__device__ __forceinline__ void chol_wide_queue(float* __restrict__ Bm, int Qp, int k0, int wide_cols,
-                                                unsigned int* __restrict__ tile_ctr, int ntiles, uint8_t* smem) {
-  __shared__ int s_tile;
-  TileSmem& sm = *reinterpret_cast<TileSmem*>(smem);
-  for (;;) {
-    __syncthreads();                       // the previous tile (or the panel role) is done with shared memory
-    if (threadIdx.x == 0) s_tile = ntiles > 0 ? (int)atomicAdd(tile_ctr, 1u) : 0;
-    __syncthreads();
-    const int t = s_tile;
-    if (t >= ntiles) break;
-    chol_wide_tile(Bm, Qp, k0, wide_cols, t, sm);
-  }
-}
-
-__global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __restrict__ Bm, int Qp, int j,
-                                                                 float* __restrict__ Ld, int apply_prev, int wide_cols,
-                                                                 unsigned int* __restrict__ tile_ctr, int ntiles) {
-  extern __shared__ __align__(16) uint8_t step_smem[];
-  const int tid = threadIdx.x;
-  const int nb = Qp / NB, k0 = j * NB;
-  const int npanel = nb - j;
-  if ((int)blockIdx.x >= npanel) {
-    chol_wide_queue(Bm, Qp, k0, wide_cols, tile_ctr, ntiles, step_smem);
     return;
   }
   // -------------------------------------------------------------- panel role
@@ -394,7 +370,6 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
   if (b == 0) {
     float* dst = Ld + (size_t)j * NB * NB;
     for (int e = tid; e < NB * NB; e += kPotfThreads) dst[e] = S.As.a[e >> 6][e & 63];
-    chol_wide_queue(Bm, Qp, k0, wide_cols, tile_ctr, ntiles, step_smem);   // then help with the trailing update
     return;
   }
   __syncthreads();
@@ -436,7 +411,6 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
   CPROF(4);
   for (int e = tid; e < NB * NB; e += kPotfThreads) P[(int64_t)(e >> 6) * Qp + (e & 63)] = S.Xs.a[e >> 6][e & 63];
   CPROF(5);
-  chol_wide_queue(Bm, Qp, k0, wide_cols, tile_ctr, ntiles, step_smem);   // panel work stored: help with the trailing update
 }
 
 // Linv diagonal blocks: one CTA per 64 x 64 diagonal factor (Ld[j]) -> Linv[j*64.., j*64..] (ld = ldd).
@@ -588,7 +562,7 @@ int launch_vbs(const double* scal, int64_t n_total, int Q, int L, float* vbs, cu
 // same factorisation twice per epoch, at :235 and inside :166; the caller caches this buffer).
 struct FactorLayout {
   int Qp;
-  size_t off_bm, off_linv, off_tm, off_ld, off_part, off_amax, off_ctr, off_tn, total;
+  size_t off_bm, off_linv, off_tm, off_ld, off_part, off_amax, off_tn, total;
   size_t tn_bytes;
 };
 
@@ -603,7 +577,6 @@ static FactorLayout factor_layout(int Q) {
   f.off_ld = o;   o += align_up((size_t)f.Qp * NB * sizeof(float), 256);   // the 64 x 64 diagonal factors
   f.off_part = o; o += align_up((size_t)kSumsqBlocks * sizeof(double), 256);
   f.off_amax = o; o += 256;
-  f.off_ctr = o;  o += align_up((size_t)(f.Qp / NB) * sizeof(unsigned int), 256);   // tile queue heads, one per panel step
   f.off_tn = o;
   f.tn_bytes = tn_workspace_bytes(Q, Q, Q, 0, 1);
   if (tc_pass1_supported(Q, Q, 0)) {
@@ -671,8 +644,6 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
   // ---- blocked Cholesky with look-ahead: ONE kernel per 64-wide panel (see chol_step_kernel); the diagonal factors
   //      are parked in Ld so that no CTA reads a block another one rewrites
   float* Ld = reinterpret_cast<float*>(base + f.off_ld);
-  unsigned int* tile_ctr = reinterpret_cast<unsigned int*>(base + f.off_ctr);
-  GPP_CUDA(cudaMemsetAsync(tile_ctr, 0, (size_t)nb * sizeof(unsigned int), st));
   {   // per device: a second device in the process needs its own attribute
     static std::mutex mu;
     static bool step_attr[64] = {false};
@@ -709,11 +680,7 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
       wide_cols = apply_prev ? blk_end - (j + 1) : 0;                 // column blocks j+1 .. blk_end-1 of this outer block
       wide_ctas = wide_cols > 0 ? (Qp - (j + 1) * NB + BM - 1) / BM : 0;
     }
-    // wide_ctas tiles in this step's queue; CTAs beyond two per SM would only wait for a slot and then find it empty
-    const int slots = 2 * sm_count() - npanel;
-    const int nwide = wide_ctas < slots ? wide_ctas : (slots > 0 ? slots : 0);
-    chol_step_kernel<<<npanel + nwide, kPotfThreads, kStepSmemBytes, st>>>(Bm, Qp, j, Ld, apply_prev, wide_cols, tile_ctr + j,
-                                                                            wide_ctas);
+    chol_step_kernel<<<npanel + wide_ctas, kPotfThreads, kStepSmemBytes, st>>>(Bm, Qp, j, Ld, apply_prev, wide_cols);
     GPP_LAUNCH_CHECK();
     if (outer && j + 1 == blk_end && blk_end < nb) {
       // rank-(kOuter * 64) update of everything right of the outer block
