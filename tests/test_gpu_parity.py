@@ -554,3 +554,31 @@ def test_outlier_rows_do_not_saturate(dev, sv, sx):
     Xb = ops.x_minus_am(X, L, V, Q, W, L, n, Q, L, 1.0)
     refx = X.double() - V.double() @ W.double()
     assert rel_err(Xb.cpu(), refx.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("N,p,q,L", [(20000, 32, 16, 256), (100000, 64, 16, 256)])
+def test_bitwise_reproducible_run_to_run(dev, N, p, q, L):
+    """compute-sanitizer is closed on this pool (profiles/r02_sanitizer_closed.txt), so races are hunted the other way:
+    the whole evaluation -- Khatri-Rao map + planes, pass 1 (split-K, fixed-order reduction), Cholesky with look-ahead,
+    solve, pass 2 -- must be BIT-identical run to run (six runs; a shared-memory or barrier race in the pipelines shows
+    up as a flipped bit long before it shows up as a wrong answer).  Also the round-1 leftover this guards against: an
+    intermittent 6e-4 error when raw slots were handed back before the converters' loads had completed."""
+    import gppvae_b200
+    from gppvae_b200.synth import make_problem
+    pr = make_problem(N, p, q, L, kind="trained", lvs=(0.4, -0.6), seed=2, device=dev)
+    vm = gppvae_b200.Vmodel(pr.x0.shape[0], q, p, q).to(dev)
+    gp = gppvae_b200.GP().to(dev)
+    with torch.no_grad():
+        vm.x0.copy_(pr.x0); vm.v0.copy_(pr.v0); gp.lvs.copy_(pr.lvs)
+    ref = None
+    for it in range(6):
+        with torch.no_grad():
+            V = vm(pr.d, pr.w)
+            Xb, Vbs, vbs, nll = gp.taylor_coeff(pr.Z, [V], need_vb=(it % 2 == 0))
+        got = (V, gp._cache.G.clone(), Xb, nll, vbs) + ((Vbs[0],) if it % 2 == 0 else ())
+        if ref is None:
+            ref = got
+        else:
+            for a, b in zip(got, ref):
+                assert torch.equal(a, b)
+        gp.invalidate_cache()
