@@ -20,6 +20,9 @@ dev = torch.device("cuda:0")
 quick = "--quick" in sys.argv
 Qs = [256, 1024, 4096] if quick else [256, 512, 1024, 2048, 4096, 8192, 16384]
 Ns = [10_000, 1_000_000] if quick else [10_000, 100_000, 1_000_000, 4_000_000]
+points = None
+if os.environ.get("SWEEP_POINTS"):      # e.g. SWEEP_POINTS=4000000x4096,1000000x16384: only these (N x Q) points
+    points = {tuple(int(v) for v in pt.split("x")) for pt in os.environ["SWEEP_POINTS"].split(",")}
 L, q = 256, 16
 peaks = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
 P_TF32 = peaks["bf16_tflops_sustained"] / 2 * 1e12
@@ -60,6 +63,8 @@ def timed(fn, gp=None, steps=10):
 for Q in Qs:
     p = Q // q
     for N in Ns:
+        if points is not None and (N, Q) not in points:
+            continue
         need_dense = 8.0 * N * Q + 12.0 * N * L + 4.0 * 4 * Q * Q + (1 << 30)
         free, total = torch.cuda.mem_get_info()
         row = dict(N=N, Q=Q, p=p)
@@ -80,9 +85,17 @@ for Q in Qs:
                     return gp.taylor_coeff(pr.Z, [vm.lazy(pr.d, pr.w)], need_vb=False)
 
             xd = None
-            if need_dense < 0.9 * free:
-                ms_d, st = timed(dense, gp)
-                xd = dense()[0]
+            fits = need_dense < 0.9 * free
+            if fits:
+                try:
+                    ms_d, st = timed(dense, gp)
+                    xd = dense()[0]
+                except torch.cuda.OutOfMemoryError:
+                    fits = False
+                    gp.stage_hook = None
+                    gp.invalidate_cache()
+                    torch.cuda.empty_cache()
+            if fits:
                 flops = N * (Q * (Q + 1.0) + 4.0 * Q * L) + Q ** 3 / 3.0 + 2.0 * Q * Q * L
                 nbytes = N * (12.0 * Q + 12 * L + 20)
                 t_tc, t_hbm = flops / P_TF32 * 1e3, nbytes / HBM * 1e3
@@ -90,6 +103,9 @@ for Q in Qs:
                 bound = "q-space latency (Cholesky chain)" if qspace > 0.5 * ms_d else ("tensor" if t_tc > t_hbm else "hbm")
                 row.update(dense_ms=ms_d, dense_msamples_s=N / ms_d / 1e3, stage_ms=st, roofline_ms=max(t_tc, t_hbm),
                            t_tensor_ms=t_tc, t_hbm_ms=t_hbm, frac_of_roofline=max(t_tc, t_hbm) / ms_d, bound=bound)
+            elif need_dense < 0.9 * free:
+                row.update(dense_ms=None, note=f"dense route ran out of memory ({need_dense / 1e9:.0f} GB for V + operand planes "
+                                               "plus the generator's and the factorisation's buffers): structured only")
             else:
                 row.update(dense_ms=None, note=f"dense route needs {need_dense / 1e9:.0f} GB (V + operand planes): structured only")
             gp.invalidate_cache()
@@ -109,7 +125,7 @@ for Q in Qs:
             del pr
             gp = vm = xd = None
             torch.cuda.empty_cache()
-        json.dump(rows, open("gpurun_out/sweep.json", "w"), indent=1)
+        json.dump(rows, open(os.environ.get("SWEEP_OUT", "gpurun_out/sweep.json"), "w"), indent=1)
 
 print("\n| N | Q | dense ms (M samples/s) | KR / pass 1 / factor / solve / pass 2 ms | roofline ms (bound) | frac | structured ms (M samples/s) | Xb structured vs dense |")
 print("|---|---|---|---|---|---|---|---|")

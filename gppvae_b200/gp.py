@@ -126,31 +126,37 @@ class _FactorCache:
     """One-entry cache of (G, factorisation) keyed on the identity and version of V and of the variances.
 
     train_gppvae.py factors the same (Vt, vs) twice per epoch (:235 via U_UBi_Shb, then :166 inside
-    taylor_coeff).  The entry keeps a reference to V's storage so the address cannot be recycled while
-    the entry is alive; in-place updates of V or lvs bump their version counters and miss.
+    taylor_coeff).  What keeps V's address from being recycled while the entry is alive: for matrices that have operand
+    planes, the planes registry (`ops.PLANES`) -- the entry remembers WHICH planes object it was built from and is valid
+    only while the registry still returns that very object for V (so dropping the registry entry, which
+    `Vmodel.forward` does before it allocates the next V of the same shape, also retires this entry, and no second
+    reference keeps last epoch's 16 GB alive); for small matrices the entry holds V itself.  In-place updates of V or lvs
+    bump their version counters and miss; the variances are compared value for value as well.
     """
 
     def __init__(self):
         self.key = None
         self.keep = None
+        self.token = None
         self.G = None
         self.ldg = 0
         self.fac: Optional[ops.Factorisation] = None
 
-    def lookup(self, key, want_binv: bool, vs: torch.Tensor):
-        if self.key is not None and self.key == key and (self.fac.Binv is not None or not want_binv):
+    def lookup(self, key, want_binv: bool, vs: torch.Tensor, token=None):
+        if self.key is not None and self.key == key and token is self.token and \
+                (self.fac.Binv is not None or not want_binv):
             # version counters do not see writes through `.data` (the reference itself initialises parameters that way,
             # vmod.py:37-40): a hit also needs the variances the factorisation was built with, value for value
             if torch.equal(self.vs_snapshot, vs.detach().to(torch.float32)):
                 return self.fac
         return None
 
-    def store(self, key, keep, G, ldg, fac, vs: torch.Tensor):
-        self.key, self.keep, self.G, self.ldg, self.fac = key, keep, G, ldg, fac
+    def store(self, key, keep, G, ldg, fac, vs: torch.Tensor, token=None):
+        self.key, self.keep, self.G, self.ldg, self.fac, self.token = key, keep, G, ldg, fac, token
         self.vs_snapshot = vs.detach().to(torch.float32).clone()
 
     def clear(self):
-        self.key = self.keep = self.G = self.fac = None
+        self.key = self.keep = self.G = self.fac = self.token = None
 
 
 class GP(nn.Module):
@@ -245,7 +251,7 @@ class GP(nn.Module):
         use_planes = ops.planes_supported(n, Q, Lk)
         pV = ops.planes_of(Vm, ldv) if use_planes else None
         pX = ops.split_planes(Xm, ldx, n, Lk) if (use_planes and Lk) else None
-        fac = self._cache.lookup(key, want_binv, vs)
+        fac = self._cache.lookup(key, want_binv, vs, token=pV)
         if fac is not None:
             self.cache_hits += 1
             C = None
@@ -260,7 +266,8 @@ class GP(nn.Module):
         self._stage("allreduce:end")
         fac = ops.factor(GC, Q + Lk, Q, vs, want_binv)
         self._stage("factor:end")
-        self._cache.store(key, (Vm, keep_vs), GC, Q + Lk, fac, vs)
+        # with planes the registry entry pins V (see _FactorCache); without, the cache entry does
+        self._cache.store(key, (None if use_planes else Vm, keep_vs), GC, Q + Lk, fac, vs, token=pV)
         return fac, (GC[:, Q:] if Lk else None), pV
 
     # ------------------------------------------------------------------ structured route (vmod.KhatriRao)

@@ -111,6 +111,29 @@ def test_structured_eval_step_calls(dev):
     assert rel_err(U.dense().cpu(), Ud.dense().cpu()) < 1e-6
 
 
+def test_structured_nll_under_autograd(dev):
+    """gp.nll(Z, [vm.lazy(d, w)]).sum().backward(): the factored V is a detached snapshot (no gradient flows to it); the
+    gradients to X and lvs must equal the dense route's (this used to raise in save_for_backward)."""
+    from gppvae_b200.synth import make_problem
+    pr = make_problem(2500, 32, 8, 64, kind="trained", lvs=(0.5, -1.0), seed=6)
+    vm, gp = _models(pr, 32, 8, dev)
+    d, w, Z = pr.d.to(dev), pr.w.to(dev), pr.Z.to(dev)
+    x1 = Z.clone().requires_grad_(True)
+    gp.lvs.grad = None
+    out = gp.nll(x1, [vm.lazy(d, w)])
+    out.sum().backward()
+    g_lvs = gp.lvs.grad.clone()
+    with torch.no_grad():
+        Vd = vm(d, w)
+    x2 = Z.clone().requires_grad_(True)
+    gp.lvs.grad = None
+    gp.nll(x2, [Vd]).sum().backward()
+    assert rel_err(x1.grad.cpu(), x2.grad.cpu()) < GRAD_TOL
+    assert rel_err(g_lvs.cpu(), gp.lvs.grad.cpu()) < 1e-3
+    with torch.no_grad():                       # no gradient requested anywhere: the forward alone
+        assert rel_err(gp.nll(Z, [vm.lazy(d, w)]).cpu(), out.detach().cpu()) < 1e-5
+
+
 def test_structured_bad_index_gives_nan_row(dev):
     import gppvae_b200
     vm = gppvae_b200.Vmodel(10, 4, 8, 4).to(dev)
