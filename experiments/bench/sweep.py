@@ -71,6 +71,8 @@ for Q in Qs:
         pr = gp = vm = None
         try:
             pr = make_problem(N, p, q, L, seed=0, device=dev)
+            torch.cuda.empty_cache()          # the generator's chunk buffers: give them back before the big allocations
+            free, total = torch.cuda.mem_get_info()
             vm = gppvae_b200.Vmodel(pr.x0.shape[0], q, p, q).to(dev)
             gp = gppvae_b200.GP().to(dev)
             with torch.no_grad():

@@ -383,6 +383,15 @@ pl_rows_kernel(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant_
       unsigned long long acc2[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc2[i] = 0ull;
+      if (p.mode == 0) {   // this thread's row of X for the epilogue: ask L2 for it now, behind the unit's MMAs
+        const int64_t prow = rt * kTileM + rank * 128 + q * 32 + lane;
+        if (prow < p.n) {
+          const float* xr = p.X + prow * p.ldx + ct * kTileN + cb * 128;
+#pragma unroll
+          for (int i = 0; i < 128; i += 32)
+            if (ct * kTileN + cb * 128 + i < p.ncols) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + i));
+        }
+      }
       for (int st = 0; st < nst * kSub; ++st, ++w) drain_window(sm, tmem, tempty0, w, acc2);
       float acc[128];
 #pragma unroll
@@ -399,20 +408,33 @@ pl_rows_kernel(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant_
           float quad = 0.f;
           const float* xr = p.X + row * p.ldx + col0;
           float* orow = p.out + row * p.ldo + col0;
+          // X and out may be the same matrix (in-place updates), so the compiler keeps every load behind the previous
+          // store: read X in batches of 8 x 128 bit, all loads of a batch before its first store (4 exposed round trips
+          // per unit instead of 32 -- the drain warps are what the issuer waits for at the end of a unit)
 #pragma unroll
-          for (int i = 0; i < 128; i += 4) {
-            if (col0 + i < p.ncols) {
-              const float4 x = *reinterpret_cast<const float4*>(xr + i);
-              float4 o;
-              o.x = (x.x - os * acc[i + 0]) * alpha;
-              o.y = (x.y - os * acc[i + 1]) * alpha;
-              o.z = (x.z - os * acc[i + 2]) * alpha;
-              o.w = (x.w - os * acc[i + 3]) * alpha;
-              *reinterpret_cast<float4*>(orow + i) = o;
-              quad = fmaf(x.x, o.x, quad); quad = fmaf(x.y, o.y, quad);
-              quad = fmaf(x.z, o.z, quad); quad = fmaf(x.w, o.w, quad);
-              xb2 = fmaf(o.x, o.x, xb2); xb2 = fmaf(o.y, o.y, xb2);
-              xb2 = fmaf(o.z, o.z, xb2); xb2 = fmaf(o.w, o.w, xb2);
+          for (int b8 = 0; b8 < 128; b8 += 32) {
+            float4 xv[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              xv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col0 + b8 + 4 * t < p.ncols) xv[t] = *reinterpret_cast<const float4*>(xr + b8 + 4 * t);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const int i = b8 + 4 * t;
+              if (col0 + i < p.ncols) {
+                const float4 x = xv[t];
+                float4 o;
+                o.x = (x.x - os * acc[i + 0]) * alpha;
+                o.y = (x.y - os * acc[i + 1]) * alpha;
+                o.z = (x.z - os * acc[i + 2]) * alpha;
+                o.w = (x.w - os * acc[i + 3]) * alpha;
+                *reinterpret_cast<float4*>(orow + i) = o;
+                quad = fmaf(x.x, o.x, quad); quad = fmaf(x.y, o.y, quad);
+                quad = fmaf(x.z, o.z, quad); quad = fmaf(x.w, o.w, quad);
+                xb2 = fmaf(o.x, o.x, xb2); xb2 = fmaf(o.y, o.y, xb2);
+                xb2 = fmaf(o.z, o.z, xb2); xb2 = fmaf(o.w, o.w, xb2);
+              }
             }
           }
           if (p.quad_part) p.quad_part[(int64_t)(ct * 2 + cb) * p.n + row] = quad;

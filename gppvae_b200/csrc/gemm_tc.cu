@@ -776,20 +776,32 @@ tc_rows_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           float quad = 0.f;
           const float* xr = p.X + row * p.ldx + col0;
           float* orow = p.out + row * p.ldo + col0;
+          // X and out may be the same matrix (the Cholesky's in-place rank-k update), so the compiler keeps every load
+          // behind the previous store: read X in batches of 8 x 128 bit, all loads of a batch before its first store
 #pragma unroll
-          for (int i = 0; i < 128; i += 4) {
-            if (col0 + i < p.ncols) {
-              const float4 x = *reinterpret_cast<const float4*>(xr + i);
-              float4 o;
-              o.x = (x.x - acc[i + 0]) * alpha;
-              o.y = (x.y - acc[i + 1]) * alpha;
-              o.z = (x.z - acc[i + 2]) * alpha;
-              o.w = (x.w - acc[i + 3]) * alpha;
-              *reinterpret_cast<float4*>(orow + i) = o;
-              quad = fmaf(x.x, o.x, quad); quad = fmaf(x.y, o.y, quad);
-              quad = fmaf(x.z, o.z, quad); quad = fmaf(x.w, o.w, quad);
-              xb2 = fmaf(o.x, o.x, xb2); xb2 = fmaf(o.y, o.y, xb2);
-              xb2 = fmaf(o.z, o.z, xb2); xb2 = fmaf(o.w, o.w, xb2);
+          for (int b8 = 0; b8 < 128; b8 += 32) {
+            float4 xv[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              xv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (col0 + b8 + 4 * t < p.ncols) xv[t] = *reinterpret_cast<const float4*>(xr + b8 + 4 * t);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const int i = b8 + 4 * t;
+              if (col0 + i < p.ncols) {
+                const float4 x = xv[t];
+                float4 o;
+                o.x = (x.x - acc[i + 0]) * alpha;
+                o.y = (x.y - acc[i + 1]) * alpha;
+                o.z = (x.z - acc[i + 2]) * alpha;
+                o.w = (x.w - acc[i + 3]) * alpha;
+                *reinterpret_cast<float4*>(orow + i) = o;
+                quad = fmaf(x.x, o.x, quad); quad = fmaf(x.y, o.y, quad);
+                quad = fmaf(x.z, o.z, quad); quad = fmaf(x.w, o.w, quad);
+                xb2 = fmaf(o.x, o.x, xb2); xb2 = fmaf(o.y, o.y, xb2);
+                xb2 = fmaf(o.z, o.z, xb2); xb2 = fmaf(o.w, o.w, xb2);
+              }
             }
           }
           if (p.quad_part) p.quad_part[(int64_t)(ct * 2 + cb) * p.n + row] = quad;

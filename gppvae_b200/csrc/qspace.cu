@@ -263,20 +263,48 @@ __global__ void __launch_bounds__(kPotfThreads, 2) chol_step_kernel(float* __res
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) acc[i][jj] = 0.f;
-    tile_mainloop<false, false>(A, B, NB, sm, acc);
+    // the output tile comes from L2 / HBM: ask for it now, behind the main loop
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = acc_row(i);
       if (r >= A.mn_valid) continue;
-      float* crow = Bm + (int64_t)(r0 + r) * Qp + c0;
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int c = acc_col(jj * 4);
-        if (c >= B.mn_valid) continue;   // mn_valid is a multiple of 64, so a float4 never straddles the edge
-        float4* c4 = reinterpret_cast<float4*>(crow + c);
-        float4 v = *c4;
-        v.x -= acc[i][jj * 4 + 0]; v.y -= acc[i][jj * 4 + 1]; v.z -= acc[i][jj * 4 + 2]; v.w -= acc[i][jj * 4 + 3];
-        *c4 = v;
+        if (c < B.mn_valid)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Bm + (int64_t)(r0 + r) * Qp + c0 + c));
+      }
+    }
+    tile_mainloop<false, false>(A, B, NB, sm, acc);
+    // read-modify-write of the tile in two batches of 8 x 128 bit: all loads of a batch before its first store (one
+    // exposed round trip per batch; load -> subtract -> store row by row was sixteen of them -- ncu: 34 % of the kernel's
+    // stall samples sat on these subtractions, profiles/r02_chol_step_q4096_ncu_full.txt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 v[4][2];
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const int r = acc_row(4 * h + ii);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int c = acc_col(jj * 4);
+          v[ii][jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < A.mn_valid && c < B.mn_valid)   // mn_valid is a multiple of 64, so a float4 never straddles the edge
+            v[ii][jj] = *reinterpret_cast<const float4*>(Bm + (int64_t)(r0 + r) * Qp + c0 + c);
+        }
+      }
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const int i = 4 * h + ii, r = acc_row(i);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int c = acc_col(jj * 4);
+          if (r < A.mn_valid && c < B.mn_valid) {
+            float4 o = v[ii][jj];
+            o.x -= acc[i][jj * 4 + 0]; o.y -= acc[i][jj * 4 + 1]; o.z -= acc[i][jj * 4 + 2]; o.w -= acc[i][jj * 4 + 3];
+            *reinterpret_cast<float4*>(Bm + (int64_t)(r0 + r) * Qp + c0 + c) = o;
+          }
+        }
       }
     }
     return;
