@@ -403,6 +403,15 @@ def run_ours(args):
             stages.setdefault("khatri_rao", []).append(ea.elapsed_time(eb))
     stage_ms = {k: sum(v) / len(v) for k, v in stages.items()}
 
+    # ---- the same step replayed from a CUDA graph (launch-bound shapes; reported beside the eager number)
+    ms_graph = None
+    if world == 1 and args.workload != "c3":
+        from gppvae_b200.graph import CapturedGPTerm
+        cap = CapturedGPTerm(vm, gp, pr.d, pr.w, pr.Z)
+        ms_graph, _ = timed(lambda: cap(), args.steps, 3)
+        del cap
+        gp.invalidate_cache()
+
     # ---- full taylor_coeff (adds B^-1, Vb): reported, not the headline
     def full_step():
         with torch.no_grad():
@@ -634,7 +643,7 @@ def run_ours(args):
                      "whole_step_frac_of_roofline": t_roof / ms, "whole_step_roofline_ms": t_roof,
                      "whole_step_frac_of_roofline_at_executed_passes": t_roof_k3 / ms,
                      "whole_step_roofline_ms_at_executed_passes": t_roof_k3},
-        "stage_ms": stage_ms, "nll_mean": nll_mean, "xb_sumsq": xb_sq, "vbs": vbs_host,
+        "stage_ms": stage_ms, "cuda_graph_ms_per_step": ms_graph, "nll_mean": nll_mean, "xb_sumsq": xb_sq, "vbs": vbs_host,
         "full_taylor_coeff": None if ms_full is None else {"ms_per_step": ms_full, "value": N / (ms_full * 1e-3)},
         "structured_route": structured, "multi_gpu_check": check,
     }

@@ -582,3 +582,34 @@ def test_bitwise_reproducible_run_to_run(dev, N, p, q, L):
             for a, b in zip(got, ref):
                 assert torch.equal(a, b)
         gp.invalidate_cache()
+
+
+def test_cuda_graph_capture_of_the_evaluation(dev):
+    """gppvae_b200.graph.CapturedGPTerm: the captured evaluation replays bit-identically to the eager one, follows new
+    inputs copied into its static buffers and parameter updates made between replays."""
+    import gppvae_b200
+    from gppvae_b200.graph import CapturedGPTerm
+    from gppvae_b200.synth import make_problem
+    pr = make_problem(4005, 64, 9, 256, kind="trained", lvs=(0.2, -0.4), seed=8, device=dev)
+    vm = gppvae_b200.Vmodel(pr.x0.shape[0], 9, 64, 9).to(dev)
+    gp = gppvae_b200.GP().to(dev)
+    with torch.no_grad():
+        vm.x0.copy_(pr.x0); vm.v0.copy_(pr.v0); gp.lvs.copy_(pr.lvs)
+
+    def eager(Z):
+        with torch.no_grad():
+            return gp.taylor_coeff(Z, [vm(pr.d, pr.w)], need_vb=False)
+
+    Xb0, _, vbs0, nll0 = eager(pr.Z)
+    step = CapturedGPTerm(vm, gp, pr.d, pr.w, pr.Z)
+    Xb, _, vbs, nll = step()
+    assert torch.equal(Xb, Xb0) and torch.equal(nll, nll0) and torch.equal(vbs, vbs0)
+    Z2 = (pr.Z * 0.5 + 0.1).contiguous()
+    Xb, _, vbs, nll = step(Z=Z2)
+    Xb2, _, vbs2, nll2 = eager(Z2)
+    assert torch.equal(Xb, Xb2) and torch.equal(nll, nll2)
+    with torch.no_grad():
+        gp.lvs.add_(torch.tensor([0.3, -0.2], device=dev))      # an optimiser step between replays
+    Xb, _, vbs, nll = step()
+    Xb3, _, vbs3, nll3 = eager(Z2)
+    assert torch.equal(Xb, Xb3) and torch.equal(nll, nll3) and torch.equal(vbs, vbs3)
