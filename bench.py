@@ -16,7 +16,7 @@ gp.py / vmod.py from the git-ignored copy under baseline/_ref/ (`__graft_entry__
 /root/reference is mounted; it travels to the GPU box with the snapshot), falling back to the op-for-op port in
 oracle/gp_oracle.py (`kind: "port"`).  Each step evaluates a fixed 100k-row sample of the workload.
 
-`--check` (any --gpus): parity of the multi-GPU path on the real collective -- all ranks' all-reduced GC and W
+`--check` (any --gpus): parity of the multi-GPU path on the real collective -- all ranks' all-reduced G, C and W
 bit-identical, sum(nll) / Xb rows against the unsharded evaluation on rank 0; a failure fails the run.
 """
 from __future__ import annotations
@@ -278,12 +278,12 @@ def run_check(args, gp, vm, pr, cfg, world, rank, dev):
     with torch.no_grad():
         V = vm(pr.d, pr.w)
         Xb, _, vbs, nll = gp.taylor_coeff(pr.Z, [V], need_vb=False)
-    GC = gp._cache.G
-    W = ops.solve_w(gp._cache.fac, GC[:, p * q:], GC.stride(0), L, L, N)[0]
+    G, C = gp._cache.G[:, : p * q], gp._cache.C
+    W = ops.solve_w(gp._cache.fac, C, C.stride(0), L, L, N)[0]
     ok = True
     report = {}
     if world > 1:
-        for name, t in (("GC", GC), ("W", W)):
+        for name, t in (("G", G.contiguous()), ("C", C.contiguous()), ("W", W)):
             lo, hi = t.clone(), t.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)

@@ -140,6 +140,7 @@ class _FactorCache:
         self.token = None
         self.G = None
         self.ldg = 0
+        self.C = None                # V^T X of the evaluation that built the entry (bench.run_check reads it)
         self.fac: Optional[ops.Factorisation] = None
 
     def lookup(self, key, want_binv: bool, vs: torch.Tensor, token=None):
@@ -156,7 +157,7 @@ class _FactorCache:
         self.vs_snapshot = vs.detach().to(torch.float32).clone()
 
     def clear(self):
-        self.key = self.keep = self.G = self.fac = self.token = None
+        self.key = self.keep = self.G = self.C = self.fac = self.token = None
 
 
 class GP(nn.Module):
@@ -179,6 +180,7 @@ class GP(nn.Module):
         self._vs_version = -1
         self.cache_hits = 0
         self.stage_hook = None       # optional callable(name): bench.py records CUDA events at stage boundaries
+        self.overlap_exchange = True  # row shards: all-reduce G beside V^T X, C beside the Cholesky (see _factorise)
 
     # ------------------------------------------------------------------ sharding
     def shard_rows(self, process_group=None, n_total: Optional[int] = None) -> "GP":
@@ -198,10 +200,13 @@ class GP(nn.Module):
         self._cache.clear()
         ops.PLANES.invalidate()
 
-    def _all_reduce(self, t: torch.Tensor) -> None:
+    def _all_reduce(self, t: torch.Tensor, async_op: bool = False):
+        """SUM over the row shards.  `async_op=True` returns the collective's work handle (None when not sharded): the
+        caller keeps launching on its stream and calls `.wait()` where the result is first needed."""
         if self._sharded:
             import torch.distributed as dist
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._group)
+            return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._group, async_op=async_op)
+        return None
 
     def _n_total(self, n: int, device) -> int:
         if not self._sharded:
@@ -250,15 +255,39 @@ class GP(nn.Module):
         key = (Vm.untyped_storage().data_ptr(), Vm.storage_offset(), Vm._version, n, Q, ldv, tok)
         use_planes = ops.planes_supported(n, Q, Lk)
         pV = ops.planes_of(Vm, ldv) if use_planes else None
-        pX = ops.split_planes(Xm, ldx, n, Lk) if (use_planes and Lk) else None
+
+        def vtx():
+            if use_planes:
+                return ops.atb_planes(pV, ops.split_planes(Xm, ldx, n, Lk), n, Q, Lk)
+            return ops.atb(Vm, ldv, Xm, ldx, n, Q, Lk)
+
         fac = self._cache.lookup(key, want_binv, vs, token=pV)
         if fac is not None:
             self.cache_hits += 1
             C = None
             if Lk:
-                C = ops.atb_planes(pV, pX, n, Q, Lk) if use_planes else ops.atb(Vm, ldv, Xm, ldx, n, Q, Lk)
+                C = vtx()
                 self._all_reduce(C)
             return fac, C, pV
+        if self._sharded and Lk and self.overlap_exchange:
+            # Row shards: the exchange step rides beside the work that does not need it.  Gram tiles -> all-reduce of G on
+            # the collective's own stream WHILE this stream splits X and forms V^T X -> all-reduce of the small C WHILE
+            # the Cholesky runs.  Only the tail of the first collective and nothing of the second stay exposed.
+            self._stage("pass1:start")
+            G = ops.gram_vtz_planes(pV, None, n, Q, 0) if use_planes else ops.gram_vtz(Vm, ldv, None, 0, n, Q, 0)
+            hG = self._all_reduce(G, async_op=True)
+            C = vtx()
+            self._stage("pass1:end")
+            hC = self._all_reduce(C, async_op=True)
+            hG.wait()
+            self._stage("allreduce:end")
+            fac = ops.factor(G, Q, Q, vs, want_binv)
+            hC.wait()
+            self._stage("factor:end")
+            self._cache.store(key, (None if use_planes else Vm, keep_vs), G, Q, fac, vs, token=pV)
+            self._cache.C = C
+            return fac, C, pV
+        pX = ops.split_planes(Xm, ldx, n, Lk) if (use_planes and Lk) else None
         self._stage("pass1:start")
         GC = ops.gram_vtz_planes(pV, pX, n, Q, Lk) if use_planes else ops.gram_vtz(Vm, ldv, Xm, ldx, n, Q, Lk)
         self._stage("pass1:end")
@@ -268,6 +297,7 @@ class GP(nn.Module):
         self._stage("factor:end")
         # with planes the registry entry pins V (see _FactorCache); without, the cache entry does
         self._cache.store(key, (None if use_planes else Vm, keep_vs), GC, Q + Lk, fac, vs, token=pV)
+        self._cache.C = GC[:, Q:] if Lk else None
         return fac, (GC[:, Q:] if Lk else None), pV
 
     # ------------------------------------------------------------------ structured route (vmod.KhatriRao)
