@@ -494,7 +494,7 @@ __device__ __forceinline__ void split4(const float4 v, float sc, uint2& h, uint2
   l.y = pack_f16x2((v.z - hz) * sc, (v.w - hw) * sc);
 }
 
-constexpr int kSplitRowBlocks = 8;   // CTAs per SM's worth of row blocks (grid.y = this x SMs / grid.x)
+constexpr int kSplitRowBlocks = 8;   // upper bound of resident 256-thread CTAs per SM (2048 threads)
 
 // fp32 matrix -> planes (+ optional per-row-block column sums of squares, fp64).  Thread = one float4 column group,
 // walking the rows of its block: coalesced 16-byte loads, 8-byte stores into each plane.
@@ -527,75 +527,114 @@ split_planes_kernel(const float* __restrict__ X, int64_t ldx, int64_t n, int col
 
 // Khatri-Rao map (vmod.py:28-35) writing V (fp32, what the API returns) AND its planes AND the exact column sums of
 // squares in one sweep: same thread layout as split_planes_kernel, the thread's four (j, k) pairs are loop-invariant.
+//
+// Everything that depends on the ROW alone -- the two index loads, their range checks and the 64-bit table offsets -- is
+// the same for all 256 threads of the CTA, so one thread per row does it once per chunk of kKrChunk rows and leaves
+// {byte offset of the object row, byte offset of the view row, 1.0f or NaN} in shared memory; the row loop of a thread is
+// then one 128-bit shared-memory read, two gathers, the arithmetic and three stores.  (First version: every thread
+// loaded and checked the indices itself; ~120 instructions per row and thread, issue slots 56 % busy at 1.96 GHz, so
+// behind pass 1 -- SM clock 1.1-1.3 GHz under the power cap -- the kernel turned issue-bound: 8.07 ms against 5.98 ms
+// on a cool chip while a plain device copy of the same size only went from 4.9 to 5.5 ms; experiments/bench/kr_instep.py.)
+constexpr int kKrChunk = 256;
+struct __align__(16) KrRow {
+  long long xoff;   // bytes from xn to the row's object features
+  int woff;         // bytes from wn to the row's view features
+  float ok;         // 1.0f, or NaN for a row whose index is outside its table (the whole row of V becomes NaN)
+};
+template <bool QUAD>
 __global__ void __launch_bounds__(256)
 kr_planes_kernel(const float* __restrict__ xn, int64_t P, int p, const float* __restrict__ wn, int64_t nviews, int q,
                  const int64_t* __restrict__ d, const int64_t* __restrict__ w, int64_t n, float* __restrict__ V,
                  int64_t ldv, __half* __restrict__ H, __half* __restrict__ Lo, int64_t ldp, int64_t rows_per_block,
                  double* __restrict__ colsq_part) {
+  __shared__ KrRow rows[kKrChunk];
   const int cols = p * q;
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
-  if (c >= cols) return;
+  const bool active = c < cols;
   int j[4], k[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    j[e] = (c + e) / q;
-    k[e] = (c + e) - j[e] * q;
+    const int ce = active ? c + e : 0;
+    j[e] = ce / q;
+    k[e] = ce - j[e] * q;
   }
-  const bool quad = (q & 3) == 0;   // the four columns share j and their k are one aligned float4 of the view row
+  // QUAD (q % 4 == 0): the four columns share j and their k are one aligned float4 of the view row
+  const char* xb[4];
+  const char* wb[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    xb[e] = reinterpret_cast<const char*>(xn + j[e]);
+    wb[e] = reinterpret_cast<const char*>(wn + k[e]);
+  }
   const float sc = exp2f((float)(kF16Top - 1));   // |v| <= 1 (product of two unit-norm rows): max|v| < 2^1
-  const float qnan = __int_as_float(0x7fc00000);
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(n, r0 + rows_per_block);
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  // Rows in batches of kB: all index loads of a batch, then all table loads, then the stores -- the two dependent
-  // gathers per row are what bounds this kernel, so keep kB of them in flight per thread; the indices of the next batch
-  // are fetched behind the stores of this one.
-  constexpr int kB = 4;
-  int64_t di[kB], wi[kB];
+  char* vp = reinterpret_cast<char*>(V + r0 * ldv + c);
+  char* hp = reinterpret_cast<char*>(H + r0 * ldp + c);
+  char* lp = reinterpret_cast<char*>(Lo + r0 * ldp + c);
+  const int64_t vstep = ldv * 4, pstep = ldp * 2;
+
+  // one row: gathers (issued by the caller in batches), products, split, stores, sums of squares
+  auto finish_row = [&](const float (&x)[4], const float4 w4) {
+    const float4 v = make_float4(x[0] * w4.x, x[1] * w4.y, x[2] * w4.z, x[3] * w4.w);
+    *reinterpret_cast<float4*>(vp) = v;
+    uint2 h, l;
+    split4(v, sc, h, l);
+    *reinterpret_cast<uint2*>(hp) = h;
+    *reinterpret_cast<uint2*>(lp) = l;
+    s0 = fma((double)v.x, (double)v.x, s0); s1 = fma((double)v.y, (double)v.y, s1);
+    s2 = fma((double)v.z, (double)v.z, s2); s3 = fma((double)v.w, (double)v.w, s3);
+    vp += vstep; hp += pstep; lp += pstep;
+  };
+  auto gather = [&](const KrRow rw, float (&x)[4], float4& w4) {
+    if (QUAD) {
+      const float xv = *reinterpret_cast<const float*>(xb[0] + rw.xoff) * rw.ok;
+      x[0] = x[1] = x[2] = x[3] = xv;
+      w4 = *reinterpret_cast<const float4*>(wb[0] + rw.woff);
+    } else {
 #pragma unroll
-  for (int u = 0; u < kB; ++u) {
-    const int64_t r = min(r0 + u, r1 - 1);
-    di[u] = d[r];
-    wi[u] = w[r];
+      for (int e = 0; e < 4; ++e) x[e] = *reinterpret_cast<const float*>(xb[e] + rw.xoff) * rw.ok;
+      w4 = make_float4(*reinterpret_cast<const float*>(wb[0] + rw.woff), *reinterpret_cast<const float*>(wb[1] + rw.woff),
+                       *reinterpret_cast<const float*>(wb[2] + rw.woff), *reinterpret_cast<const float*>(wb[3] + rw.woff));
+    }
+  };
+
+  for (int64_t rc = r0; rc < r1; rc += kKrChunk) {
+    const int nr = (int)min((int64_t)kKrChunk, r1 - rc);
+    __syncthreads();                       // the previous chunk's entries have been read by everybody
+    if ((int)threadIdx.x < nr) {
+      const int64_t di = d[rc + threadIdx.x], wi = w[rc + threadIdx.x];
+      const bool ok = (di >= 0) & (di < P) & (wi >= 0) & (wi < nviews);
+      KrRow rw;
+      rw.xoff = ok ? di * (int64_t)p * 4 : 0;
+      rw.woff = ok ? (int)(wi * q * 4) : 0;
+      rw.ok = ok ? 1.f : __int_as_float(0x7fc00000);
+      rows[threadIdx.x] = rw;
+    }
+    __syncthreads();
+    if (!active) continue;
+    // rows in batches of kB: all gathers of a batch in flight before the first store
+    constexpr int kB = 4;
+    int r = 0;
+    for (; r + kB <= nr; r += kB) {
+      float x[kB][4];
+      float4 w4[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) gather(rows[r + u], x[u], w4[u]);
+#pragma unroll
+      for (int u = 0; u < kB; ++u) finish_row(x[u], w4[u]);
+    }
+    for (; r < nr; ++r) {
+      float x[4];
+      float4 w4;
+      gather(rows[r], x, w4);
+      finish_row(x, w4);
+    }
   }
-  for (int64_t rb = r0; rb < r1; rb += kB) {
-    float4 v[kB];
-#pragma unroll
-    for (int u = 0; u < kB; ++u) {
-      const bool ok = (di[u] >= 0) & (di[u] < P) & (wi[u] >= 0) & (wi[u] < nviews);
-      const float* xr = xn + (ok ? di[u] : 0) * p;
-      const float* wr = wn + (ok ? wi[u] : 0) * q;
-      float4 t;
-      if (quad) {
-        const float x = xr[j[0]];
-        const float4 w4 = *reinterpret_cast<const float4*>(wr + k[0]);
-        t = make_float4(x * w4.x, x * w4.y, x * w4.z, x * w4.w);
-      } else {
-        t = make_float4(xr[j[0]] * wr[k[0]], xr[j[1]] * wr[k[1]], xr[j[2]] * wr[k[2]], xr[j[3]] * wr[k[3]]);
-      }
-      v[u] = ok ? t : make_float4(qnan, qnan, qnan, qnan);
-    }
-#pragma unroll
-    for (int u = 0; u < kB; ++u) {   // next batch's indices
-      const int64_t r = min(rb + kB + u, r1 - 1);
-      di[u] = d[r];
-      wi[u] = w[r];
-    }
-#pragma unroll
-    for (int u = 0; u < kB; ++u) {
-      const int64_t r = rb + u;
-      if (r < r1) {
-        *reinterpret_cast<float4*>(V + r * ldv + c) = v[u];
-        uint2 h, l;
-        split4(v[u], sc, h, l);
-        *reinterpret_cast<uint2*>(H + r * ldp + c) = h;
-        *reinterpret_cast<uint2*>(Lo + r * ldp + c) = l;
-        s0 = fma((double)v[u].x, (double)v[u].x, s0); s1 = fma((double)v[u].y, (double)v[u].y, s1);
-        s2 = fma((double)v[u].z, (double)v[u].z, s2); s3 = fma((double)v[u].w, (double)v[u].w, s3);
-      }
-    }
+  if (active) {
+    double* o = colsq_part + (int64_t)blockIdx.y * cols + c;
+    o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
   }
-  double* o = colsq_part + (int64_t)blockIdx.y * cols + c;
-  o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
 }
 
 // colsq[c] = sum over the row blocks, in a fixed order; meta[1] = 1
@@ -620,15 +659,29 @@ __global__ void copy_u32_kernel(uint32_t* dst, const uint32_t* src) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
 }
 
-void split_grid(int64_t n, int cols, dim3& grid, int64_t& rows_per_block) {
+// ctas_per_sm > 0: one full wave of equal row blocks for a kernel that holds that many CTAs per SM; 0: 8 x SMs CTAs (the
+// upper bound the workspace is sized for).
+void split_grid(int64_t n, int cols, dim3& grid, int64_t& rows_per_block, int ctas_per_sm = 0) {
   const int gx = (int)ceil_div(cols, 1024);
-  int64_t gy = (int64_t)kSplitRowBlocks * sm_count() / gx;
+  if (ctas_per_sm <= 0 || ctas_per_sm > kSplitRowBlocks) ctas_per_sm = kSplitRowBlocks;
+  int64_t gy = (int64_t)ctas_per_sm * sm_count() / gx;
   if (gy < 1) gy = 1;
   if (gy > ceil_div(n, 16)) gy = ceil_div(n, 16);
   if (gy < 1) gy = 1;
   rows_per_block = ceil_div(n > 0 ? n : 1, gy);
   gy = ceil_div(n > 0 ? n : 1, rows_per_block);
   grid = dim3((unsigned)gx, (unsigned)gy);
+}
+
+// resident 256-thread CTAs per SM of a producer kernel (register-limited; static shared memory only)
+template <typename K>
+int resident_ctas_256(K kernel) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, 0) != cudaSuccess || nb <= 0) {
+    cudaGetLastError();
+    nb = 4;
+  }
+  return nb;
 }
 
 template <typename K>
@@ -696,7 +749,7 @@ int launch_split_planes(const float* X, int64_t ldx, int64_t n, int cols, void* 
   if (n <= 0) return GPP_OK;
   dim3 grid;
   int64_t rpb;
-  split_grid(n, cols, grid, rpb);
+  split_grid(n, cols, grid, rpb);   // (one wave measured here too: 5.29 -> 5.47 ms at c3 shape; the fixed grid stays)
   double* part = nullptr;
   if (want_colsq) {
     const size_t need = align_up((size_t)grid.y * cols * sizeof(double), 256);
@@ -726,16 +779,25 @@ int launch_kr_planes(const float* xn, int64_t P, int p, const float* wn, int64_t
   planes_meta_kernel<<<1, 32, 0, st>>>(pv.meta, (uint32_t)(1 - 1 + 127) << 23, 0u);   // max|v| < 2^1
   GPP_LAUNCH_CHECK();
   if (n <= 0) return GPP_OK;
+  // one full wave of equal row blocks (measured at c3, cool chip / behind pass 1: 5.89 / 7.11 ms; with the fixed
+  // 8 x SMs grid 6.40 / 8.15 ms; the first version of the kernel 5.97 / 7.67 and 6.06 / 7.44 ms)
   dim3 grid;
   int64_t rpb;
-  split_grid(n, cols, grid, rpb);
+  split_grid(n, cols, grid, rpb, (q & 3) == 0 ? resident_ctas_256(kr_planes_kernel<true>) : resident_ctas_256(kr_planes_kernel<false>));
   const size_t need = align_up((size_t)grid.y * cols * sizeof(double), 256);
   if (!ws || ws_bytes < need) {
     set_error("khatri_rao_fwd_planes: workspace too small (%zu < %zu bytes)", ws_bytes, need);
     return GPP_ERR_WORKSPACE;
   }
   double* part = static_cast<double*>(ws);
-  kr_planes_kernel<<<grid, 256, 0, st>>>(xn, P, p, wn, nviews, q, d, w, n, V, ldv, pv.hi, pv.lo, pv.ldp, rpb, part);
+  if ((int64_t)nviews * q * 4 > 0x7fffffffLL) {
+    set_error("khatri_rao_fwd_planes: view table larger than 2 GB");
+    return GPP_ERR_UNSUPPORTED;
+  }
+  if ((q & 3) == 0)
+    kr_planes_kernel<true><<<grid, 256, 0, st>>>(xn, P, p, wn, nviews, q, d, w, n, V, ldv, pv.hi, pv.lo, pv.ldp, rpb, part);
+  else
+    kr_planes_kernel<false><<<grid, 256, 0, st>>>(xn, P, p, wn, nviews, q, d, w, n, V, ldv, pv.hi, pv.lo, pv.ldp, rpb, part);
   GPP_LAUNCH_CHECK();
   colsq_reduce_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, st>>>(part, (int)grid.y, cols, pv.colsq, pv.meta);
   GPP_LAUNCH_CHECK();

@@ -409,7 +409,6 @@ static_assert(kStepSmemBytesLL <= 227 * 1024, "left-looking tile does not fit th
 
 constexpr int kLLTileFloats = BM * NB;     // one partial tile of the left-looking update
 constexpr int kLLMaxRowTiles = 64;         // counters per step (row tiles of 128 rows: padded Q up to 8192)
-constexpr int kSideSms = 32;               // SMs the left-looking grid leaves to the side stream (triangular inverse)
 constexpr int kLLMaxParts = 256;           // wide CTAs of one left-looking step (one SM each; more than any device has)
 
 constexpr int kOuterCholMinQ = 6144;   // padded Q from which the Cholesky uses 256-wide outer blocks + tensor-core updates
@@ -1079,15 +1078,23 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
   const int64_t part_cap = kLLMaxParts;
   float* ll_part = reinterpret_cast<float*>(base + f.off_llp);
   // The triangular inverse of the LEADING diagonal block [0, b_top), b_top = the largest power-of-two multiple of the
-  // panel below Qp, only needs the panels < jsplit = b_top / 64: it runs on a side stream beside the second half of the
-  // panel chain, followed by T = L21 . L11^-1 of the top level.  OFF by default (GPP_INV_OVERLAP=1 enables it): measured
-  // at Q = 4096 it costs 0.05 ms instead of saving 0.25 -- the left-looking updates keep every SM's tensor pipe busy
-  // through the middle of the chain, so the side stream's kernels only take cycles from the steps they run beside.
+  // panel below Qp, only needs the panels < jsplit = b_top / 64: it runs on a side stream beside the TAIL of the panel
+  // chain, followed by T = L21 . L11^-1 of the top level.  Where the side stream forks matters: the left-looking updates
+  // keep every SM's tensor pipe busy through the middle of the chain, and forking at jsplit - 1 (the earliest possible
+  // step) with SMs set aside for the side stream cost 0.05 ms at Q = 4096 instead of saving anything; forking at 3/4 of
+  // the chain, where few wide CTAs are left, and setting no SMs aside saves 0.06 ms (1.623 -> 1.558-1.571 ms for forks at
+  // steps 44..52; factor_only.py).  GPP_INV_OVERLAP=0 disables it, GPP_INV_FORK=<step> / GPP_INV_SIDE_SMS=<n> move it.
   int b_top = NB;
   while (b_top * 2 < Qp) b_top *= 2;
   const int jsplit = b_top / NB;
   const char* ov_env = getenv("GPP_INV_OVERLAP");
-  const bool want_side = !outer && Qp >= 1024 && ov_env && ov_env[0] == '1';
+  const bool want_side = !outer && Qp >= 1024 && !(ov_env && ov_env[0] == '0');
+  const char* fork_env = getenv("GPP_INV_FORK");
+  int fork_step = jsplit - 1 > (3 * nb) / 4 ? jsplit - 1 : (3 * nb) / 4;
+  if (fork_env && atoi(fork_env) >= jsplit - 1) fork_step = atoi(fork_env);
+  if (fork_step > nb - 1) fork_step = nb - 1;
+  const char* sms_env = getenv("GPP_INV_SIDE_SMS");
+  const int side_sms = sms_env ? atoi(sms_env) : 0;
   SideStream* side = nullptr;
   bool side_started = false;
   if (want_side) GPP_TRY(side_stream(&side));
@@ -1106,7 +1113,7 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
         // row tiles of column block j + 1, contraction over the j finished panels split so that the step's CTAs have
         // an SM each
         const int T = (int)ceil_div(Qp - (j + 1) * NB, BM);
-        int free_sms = sms - npanel - ((want_side && j >= jsplit) ? kSideSms : 0);   // the side stream's kernels need room
+        int free_sms = sms - npanel - ((want_side && j > fork_step) ? side_sms : 0);   // the side stream's kernels need room
         if (free_sms < T) free_sms = T;
         int S = free_sms / T;
         if (S > j) S = j;
@@ -1145,7 +1152,7 @@ int launch_factor(const float* G, int64_t ldg, int Q, const float* vs, uint32_t 
       chol_step_kernel<false><<<npanel + wide_ctas, kPotfThreads, kStepSmemBytes, st>>>(
           Bm, Qp, j, Ld, apply_prev, wide_cols, ll_S, ll_chunk, ll_part, counters + (size_t)j * kLLMaxRowTiles);
     GPP_LAUNCH_CHECK();
-    if (want_side && j == jsplit - 1) {
+    if (want_side && j == fork_step) {
       cudaStream_t s2 = side->s;
       GPP_CUDA(cudaEventRecord(side->fork, st));
       GPP_CUDA(cudaStreamWaitEvent(s2, side->fork, 0));

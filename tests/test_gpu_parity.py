@@ -584,14 +584,16 @@ def test_bitwise_reproducible_run_to_run(dev, N, p, q, L):
         gp.invalidate_cache()
 
 
-def test_cuda_graph_capture_of_the_evaluation(dev):
+@pytest.mark.parametrize("N,p,q", [(4005, 64, 9), (6000, 64, 16)])
+def test_cuda_graph_capture_of_the_evaluation(dev, N, p, q):
     """gppvae_b200.graph.CapturedGPTerm: the captured evaluation replays bit-identically to the eager one, follows new
-    inputs copied into its static buffers and parameter updates made between replays."""
+    inputs copied into its static buffers and parameter updates made between replays.  (Q = 1024: the factorisation
+    forks its side stream inside the capture.)"""
     import gppvae_b200
     from gppvae_b200.graph import CapturedGPTerm
     from gppvae_b200.synth import make_problem
-    pr = make_problem(4005, 64, 9, 256, kind="trained", lvs=(0.2, -0.4), seed=8, device=dev)
-    vm = gppvae_b200.Vmodel(pr.x0.shape[0], 9, 64, 9).to(dev)
+    pr = make_problem(N, p, q, 256, kind="trained", lvs=(0.2, -0.4), seed=8, device=dev)
+    vm = gppvae_b200.Vmodel(pr.x0.shape[0], q, p, q).to(dev)
     gp = gppvae_b200.GP().to(dev)
     with torch.no_grad():
         vm.x0.copy_(pr.x0); vm.v0.copy_(pr.v0); gp.lvs.copy_(pr.lvs)
