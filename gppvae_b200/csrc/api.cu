@@ -116,7 +116,9 @@ extern "C" int gpp_khatri_rao_fwd_planes(const float* xn, int64_t P, int32_t p, 
 }
 
 extern "C" size_t gpp_gram_planes_workspace_bytes(int64_t n, int32_t Q, int32_t L) {
-  return pl_pass1_workspace_bytes(n, Q, L, false);
+  // serves gpp_gram_vtz_planes (Gram tiles + V^T X) and gpp_atb_planes (no Gram tiles): their split counts differ
+  const size_t a = pl_pass1_workspace_bytes(n, Q, L, false), b = L > 0 ? pl_pass1_workspace_bytes(n, Q, L, true) : 0;
+  return a > b ? a : b;
 }
 
 extern "C" int gpp_gram_vtz_planes(const void* planesV, const void* planesX, int64_t n, int32_t Q, int32_t L,

@@ -953,20 +953,25 @@ void pass1_geometry(int64_t n, int Q, int L, bool skip_g, int pairs, int kblock,
   p.tiles_g = skip_g ? 0 : p.tm_count * (p.tm_count + 1) / 2;
   p.tn_c = (int)ceil_div(L, TN);
   p.tiles = p.tiles_g + p.tm_count * p.tn_c;
-  // choose the split count: best wave efficiency on the persistent grid of CTA pairs, >= 512 rows per split,
-  // <= 1 GB of partial tiles
+  // choose the split count on the persistent grid of CTA pairs (>= 512 rows per split, <= 1 GB of partial tiles): the
+  // smallest estimated time  units-per-pair x (rows per split + kUnitOverheadRows).  A unit ends with the drain of its
+  // accumulator and a 256 KB partial tile (and the reduction reads it back): 10-23 us, the time of ~1000 rows, measured at
+  // n = 125k, Q = 4096 (experiments/bench/shard_stages.py: V^T Z, 16 tiles, 0.80 ms as 37 splits of 3392 rows -- what pure
+  // wave efficiency picks -- against 0.64 ms as 4 splits; the 136 Gram tiles 4.51 ms at 7 splits, 4.6-4.9 ms at 1, 2, 14, 28).
+  constexpr int64_t kUnitOverheadRows = 1024;
   const int64_t max_by_rows = n / 512 > 1 ? n / 512 : 1;
   const int64_t max_by_ws = (int64_t)(1024ll << 20) / ((int64_t)(p.tiles > 0 ? p.tiles : 1) * TM * TN * 4);
   int64_t smax = max_by_rows < max_by_ws ? max_by_rows : max_by_ws;
   if (smax < 1) smax = 1;
   if (smax > 2 * pairs) smax = 2 * pairs;
   int best = 1;
-  double best_eff = 0;
+  int64_t best_cost = -1;
   for (int s = 1; s <= smax; ++s) {
-    const int64_t units = (int64_t)p.tiles * s;
-    const double eff = (double)units / (double)(ceil_div(units, pairs) * pairs);
-    if (eff > best_eff + 0.02) {   // prefer fewer splits unless efficiency improves by > 2 %
-      best_eff = eff;
+    const int64_t rps = ceil_div(ceil_div(n > 0 ? n : 1, s), kblock) * kblock;
+    const int64_t units = (int64_t)p.tiles * ceil_div(n > 0 ? n : 1, rps);
+    const int64_t cost = ceil_div(units, pairs) * (rps + kUnitOverheadRows);
+    if (best_cost < 0 || cost < best_cost) {   // ties: fewer splits
+      best_cost = cost;
       best = s;
     }
   }

@@ -349,6 +349,30 @@ def test_full_size_c2_properties(dev):
     assert rel_err(Xb[idx].cpu(), ref.cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("N,p,q,L", [(100_000, 64, 16, 256), (125_000, 256, 16, 256), (20_000, 64, 9, 100), (4005, 64, 9, 256)])
+def test_factor_first_then_right_hand_side_on_the_cached_factor(dev, N, p, q, L):
+    """train_gppvae.py:235-237 followed by :166 on the same V: `U_UBi_Shb` forms the Gram tiles alone, `solve` and the
+    next `taylor_coeff` then add V^T X as a launch of its own (no Gram tiles: a different tile list and split count than
+    the one-launch evaluation, so also a different workspace) -- same results as a fresh one-launch evaluation."""
+    import gppvae_b200
+    from gppvae_b200.synth import make_problem
+    pr = make_problem(N, p, q, L, kind="trained", lvs=(0.3, -0.2), seed=11, device=dev)
+    vm = gppvae_b200.Vmodel(pr.x0.shape[0], q, p, q).to(dev)
+    gp, gp1 = gppvae_b200.GP().to(dev), gppvae_b200.GP().to(dev)
+    with torch.no_grad():
+        vm.x0.copy_(pr.x0); vm.v0.copy_(pr.v0); gp.lvs.copy_(pr.lvs); gp1.lvs.copy_(pr.lvs)
+        V = vm(pr.d, pr.w)
+        U, UBi, _ = gp.U_UBi_Shb([V], gp.get_vs())
+        KiZ = gp.solve(pr.Z, U, UBi, gp.get_vs())
+        hits = gp.cache_hits
+        Xb, _, vbs, nll = gp.taylor_coeff(pr.Z, [V], need_vb=False)
+        assert gp.cache_hits == hits + 1
+        Xb1, _, vbs1, nll1 = gp1.taylor_coeff(pr.Z, [V], need_vb=False)
+    assert rel_err(Xb.cpu(), Xb1.cpu()) < 1e-5 and rel_err(KiZ.cpu(), Xb1.cpu()) < 1e-5
+    assert abs(nll.double().sum().item() - nll1.double().sum().item()) / abs(nll1.double().sum().item()) < 1e-6
+    assert rel_err(vbs.cpu(), vbs1.cpu()) < 1e-5
+
+
 @pytest.mark.parametrize("n,p,q,L", [(3000, 16, 8, 64), (300, 8, 4, 32)])
 def test_host_entry_matches_oracle(dev, n, p, q, L):
     """gpp_gp_term_host (the end-to-end C entry bench.py times) against the oracle: the synchronous call, then the
