@@ -313,6 +313,7 @@ struct PlRowsParams {
   float alpha_host;
   float* quad_part;    // [col_tiles * 2][n]
   double* xb2_part;    // [units * 16]
+  unsigned int* wave_ctr;  // device, zeroed before the launch: producer-units issued so far (wave alignment); may be null
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPlThreads, 1)
@@ -336,7 +337,21 @@ pl_rows_kernel(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant_
       tma_prefetch_desc(&tmA1h); tma_prefetch_desc(&tmA1l); tma_prefetch_desc(&tmBh); tma_prefetch_desc(&tmBl);
       const uint32_t full0 = smem_u32(&sm->full[0]) & 0xFEFFFFFFu;
       uint32_t it = 0;
+      // Wave alignment, as in pass 1 (a hint, not a dependency): the col_tiles pairs that work on one row tile read the
+      // same 4.4 MB of A; left alone they drift apart by more than L2 holds and every one of them fetches its A tile from
+      // DRAM again (ncu, c3 `Vb` product: 268 GB read per launch against 17.5 GB of operands).
+      bool wave_sync = p.wave_ctr != nullptr && p.col_tiles > 1;
       for (int64_t u = pair; u < nunits; u += npairs) {
+        if (wave_sync && u >= npairs) {
+          const unsigned int target = 2u * (unsigned int)min((u / npairs) * npairs, nunits);
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile unsigned int*>(p.wave_ctr) < target) {
+            if (clock64() - t0 > 4000000ll) {
+              wave_sync = false;
+              break;
+            }
+          }
+        }
         const int64_t rt = u / p.col_tiles;
         const int ct = (int)(u - rt * p.col_tiles);
         const int row = (int)(rt * kTileM) + (int)rank * 128;
@@ -361,6 +376,7 @@ pl_rows_kernel(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant_
           tma_load_2d_pair(dst + 6 * kBoxBytes, &tmBl, bcol, kb, bar);
           tma_load_2d_pair(dst + 7 * kBoxBytes, &tmBl, bcol + 64, kb, bar);
         }
+        if (p.wave_ctr) atomicAdd(p.wave_ctr, 1u);
       }
     } else if (warp == 1 && lane == 0 && rank == 0) {
       uint32_t it = 0, w = 0;
@@ -878,6 +894,10 @@ static int launch_pl_rows(const PlanesView& a1, int K1, const PlanesView* a2, in
   const int64_t nunits = p.row_tiles * p.col_tiles;
   const int pairs = (int)(nunits < pl_pairs() ? nunits : pl_pairs());
   if (pairs <= 0) return GPP_OK;
+  if (const char* e = getenv("GPP_TC_WAVE_SYNC")) {   // experiment knob: 0 switches the wave alignment off
+    if (e[0] == '0') p.wave_ctr = nullptr;
+  }
+  if (p.wave_ctr) GPP_CUDA(cudaMemsetAsync(p.wave_ctr, 0, 4, st));
   pl_rows_kernel<<<2 * pairs, kPlThreads, kPlSmemBytes, st>>>(tA1h, tA1l, tA2h, tA2l, tBh, tBl, p);
   GPP_LAUNCH_CHECK();
   return GPP_OK;
@@ -887,7 +907,8 @@ static int launch_pl_rows(const PlanesView& a1, int K1, const PlanesView* a2, in
 size_t pl_xb_workspace_bytes(int64_t n, int Q, int L) {
   const int64_t col_tiles = ceil_div(L, kTileN), row_tiles = ceil_div(n, kTileM);
   return align_up(planes_bytes(Q, L), 256) + align_up((size_t)col_tiles * 2 * n * sizeof(float), 256) +
-         align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256) + align_up(xb_finalize_bytes(), 256);
+         align_up((size_t)row_tiles * col_tiles * 16 * sizeof(double), 256) + align_up(xb_finalize_bytes(), 256) +
+         256 /* wave counter */;
 }
 
 // Xb = alpha (X - V W) from the planes of V (W is split here: Q x L, small); with nll != nullptr the NLL epilogue.
@@ -914,6 +935,7 @@ int launch_pl_xb(const void* planesV, const float* X, int64_t ldx, const float* 
   }
   const PlanesView pv = planes_view(const_cast<void*>(planesV), n, Q);
   const PlanesView pw = planes_view(planesW, Q, L);
+  p.wave_ctr = reinterpret_cast<unsigned int*>(wsb + need - 256);
   GPP_TRY(launch_pl_rows(pv, Q, nullptr, 0, pw, n, L, p, st));
   if (nll) {
     double* fin = reinterpret_cast<double*>(wsb + off);
@@ -943,7 +965,7 @@ __global__ void __launch_bounds__(256) build_bstk_scaled_kernel(const float* __r
 
 size_t pl_vb_workspace_bytes(int64_t n, int Q, int L) {
   return align_up(planes_bytes(n, L), 256) + align_up((size_t)(Q + L) * Q * sizeof(float), 256) +
-         align_up(planes_bytes(Q + L, Q), 256);
+         align_up(planes_bytes(Q + L, Q), 256) + 256 /* wave counter */;
 }
 
 int launch_pl_vb(const void* planesV, const float* Xb, int64_t ldxb, const float* Binv, const float* W, int64_t ldw,
@@ -967,6 +989,7 @@ int launch_pl_vb(const void* planesV, const float* Xb, int64_t ldxb, const float
   const PlanesView pb = planes_view(planesB, (int64_t)Q + L, Q);
   PlRowsParams p{};
   p.mode = 1; p.out = Vb; p.ldo = ldvb; p.alpha_host = 1.f;
+  p.wave_ctr = reinterpret_cast<unsigned int*>(wsb + need - 256);
   return launch_pl_rows(pv, Q, &px, L, pb, n, Q, p, st);
 }
 
