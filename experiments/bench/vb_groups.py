@@ -1,5 +1,7 @@
 """Time of the full taylor_coeff (Xb, Vb, vbs, nll) at c3 minus the evaluation without Vb: the Vb product + B^-1, for the
-column-group bound in the environment (GPP_PL_COL_GROUP_MB; 1000 = one group, the round-2 order before this experiment)."""
+column-group bound in the environment (GPP_PL_COL_GROUP_MB; 1000 = one group).  The column-group experiment itself was
+dropped from the library after this script measured it (profiles/r02_vb_wave_alignment.txt): the variable is no longer read,
+the script remains as the timing harness of the Vb product (GPP_TC_WAVE_SYNC=0 switches the producers' alignment off)."""
 import os
 import sys
 
