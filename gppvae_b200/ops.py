@@ -71,6 +71,8 @@ def as_matrix(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
     require_cuda_f32(t, name)
     t = t.detach()
     n, c = t.shape
+    if n == 0 or c == 0:
+        raise ValueError(f"{name} is empty ({n} x {c})")
     if c % 4 == 0 and t.data_ptr() % 16 == 0:
         if t.is_contiguous():
             return t, c
@@ -209,6 +211,9 @@ def khatri_rao_fwd(xn: torch.Tensor, wn: torch.Tensor, d: torch.Tensor, w: torch
     w = _check_index(w, "w", xn.device)
     if d.shape != w.shape:
         raise ValueError("d and w must have the same length")
+    if d.shape[0] == 0:
+        # the reference raises here as well (vmod.py:34 reshapes 0 elements to [0, -1])
+        raise ValueError("d and w are empty: there is no row of V to build")
     P, p = xn.shape
     nv, q = wn.shape
     Q = p * q

@@ -29,6 +29,8 @@ class KhatriRao:
         self.w = ops._check_index(w, "w", xn.device)
         if self.d.shape != self.w.shape:
             raise ValueError("d and w must have the same length")
+        if self.d.shape[0] == 0:
+            raise ValueError("d and w are empty: there is no row of V to build")
         P, p = xn.shape
         self.P, self.p_true = P, p
         self.nviews, self.q = wn.shape

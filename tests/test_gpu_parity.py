@@ -289,6 +289,25 @@ def test_out_of_range_index_gives_nan_row(dev):
     assert torch.isnan(V[1]).all() and not torch.isnan(V[0]).any() and not torch.isnan(V[2]).any()
 
 
+def test_empty_inputs_raise_cleanly(dev):
+    """The reference raises on an empty index set (vmod.py:34 cannot reshape 0 elements to [0, -1]); here every entry of the
+    path refuses empty operands with a ValueError before any launch, and the library keeps working afterwards."""
+    import gppvae_b200
+    vm = gppvae_b200.Vmodel(8, 4, 16, 8).to(dev)
+    gp = gppvae_b200.GP().to(dev)
+    d = torch.zeros(0, dtype=torch.long, device=dev)
+    with torch.no_grad():
+        for fn in (lambda: vm(d, d), lambda: vm.lazy(d, d),
+                   lambda: gp.taylor_coeff(torch.zeros(0, 32, device=dev), [torch.zeros(0, 128, device=dev)]),
+                   lambda: gp.U_UBi_Shb([torch.zeros(0, 128, device=dev)], gp.get_vs())):
+            with pytest.raises(ValueError):
+                fn()
+        dd = torch.randint(0, 8, (700,), device=dev)
+        ww = torch.randint(0, 4, (700,), device=dev)
+        out = gp.taylor_coeff(torch.randn(700, 32, device=dev), [vm(dd, ww)])
+    assert torch.isfinite(out[3]).all()
+
+
 def test_argument_errors(dev):
     import gppvae_b200
     gp = gppvae_b200.GP().to(dev)
