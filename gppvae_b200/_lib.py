@@ -74,6 +74,9 @@ _SIGNATURES = {
                        c_void_p]),
     "gpp_kr_slot_sums": (c_int, [_PF, c_int64, _PF, _PF, _PF, c_int64, c_int32, c_int32, c_int32, c_int32, _PF, c_int64,
                                  c_void_p]),
+    "gpp_kr_slot_sums_planes": (c_int, [_PF, c_int64, c_int64, _PF, _PF, _PF, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                        c_int32, _PF, c_size_t, c_void_p]),
+    "gpp_am_planes": (c_int, [_PF, _PF, c_int64, c_int32, c_int32, c_float, _PF, c_int64, _PF, c_size_t, c_void_p]),
     "gpp_kr_assemble_gc": (c_int, [_PF, c_int64, _PF, c_int32, c_int32, c_int32, c_int32, c_int32, _PF, c_int64,
                                    c_void_p]),
     "gpp_kr_assemble_m": (c_int, [_PF, c_int64, _PF, c_int32, c_int32, c_int32, c_int32, _PF, c_int64, c_void_p]),

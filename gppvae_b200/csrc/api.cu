@@ -299,6 +299,28 @@ extern "C" int gpp_vb(const float* V, int64_t ldv, const float* Xb, int64_t ldxb
   return launch_vb(V, ldv, Xb, ldxb, Binv, Q, W, ldw, scal, n, Q, L, L_true, Vb, ldvb, (cudaStream_t)stream);
 }
 
+extern "C" int gpp_kr_slot_sums_planes(const float* X, int64_t ldx, int64_t n, const int64_t* order,
+                                       const int64_t* slot_start, const float* xn, int64_t P, int32_t p, int32_t nviews,
+                                       int32_t L, int32_t with_x, int32_t max_count, void* planes, size_t planes_bytes_,
+                                       gpp_stream_t stream) {
+  GPP_REQUIRE(X && order && slot_start && xn && planes, "kr_slot_sums_planes: null pointer");
+  GPP_REQUIRE(n > 0 && P > 0 && p > 0 && nviews > 0 && L > 0 && p % 4 == 0 && L % 4 == 0 && max_count >= 0,
+              "kr_slot_sums_planes: p and L must be multiples of 4");
+  GPP_REQUIRE(mat_ok(X, ldx, L) && aligned16(xn) && planes_ok(planes), "kr_slot_sums_planes: bad leading dimension / alignment");
+  const int64_t cols = (int64_t)nviews * ((with_x ? p : 0) + L);
+  GPP_REQUIRE(cols < (1ll << 31) && planes_bytes_ >= planes_bytes(P, (int)cols), "kr_slot_sums_planes: planes buffer too small");
+  return launch_kr_slot_sums_planes(X, ldx, n, order, slot_start, xn, P, p, nviews, L, with_x, max_count, planes,
+                                    (cudaStream_t)stream);
+}
+
+extern "C" int gpp_am_planes(const void* planesA, const void* planesB, int64_t n, int32_t k, int32_t m, float alpha,
+                             float* out, int64_t ldo, void* workspace, size_t workspace_bytes, gpp_stream_t stream) {
+  GPP_REQUIRE(k > 0 && m > 0 && k % 4 == 0 && m % 4 == 0, "am_planes: k and m must be positive multiples of 4");
+  GPP_REQUIRE(pl_rows_supported(n, k, m), "am_planes: shape below the tensor-core tile");
+  GPP_REQUIRE(planes_ok(planesA) && planes_ok(planesB) && mat_ok(out, ldo, m), "am_planes: bad pointer / leading dimension");
+  return launch_pl_am(planesA, planesB, n, k, m, alpha, out, ldo, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" size_t gpp_vb_planes_workspace_bytes(int64_t n, int32_t Q, int32_t L) { return pl_vb_workspace_bytes(n, Q, L); }
 
 extern "C" int gpp_vb_planes(const void* planesV, const float* Xb, int64_t ldxb, const float* Binv, const float* W,

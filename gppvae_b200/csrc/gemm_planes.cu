@@ -675,6 +675,60 @@ __global__ void copy_u32_kernel(uint32_t* dst, const uint32_t* src) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
 }
 
+// Slot sums of the structured route (structured.cu, kr_slot_sum_kernel) written DIRECTLY as operand planes, so that the
+// P-long product xn^T [cnt (x) xn | Xs] runs on the planes kernel without the 2 GB fp32 matrix, without a magnitude scan
+// of it and without converter warps:  XZ[o, v p + j] = cnt[s] xn[o, j],  XZ[o, zcol0 + v L + l] = sum of X[i, l] over the
+// rows of slot s = o nviews + v (added in the order of `order`: deterministic).  The scale comes from a BOUND instead of a
+// scan of the result: |cnt xn| <= max_count (unit rows), |slot sum| <= max_count max|X| -- meta[0] is set by
+// slot_scale_kernel from the exact max|X| (one read of X) and the largest slot count (known to the caller from the
+// index).  One warp per slot.
+__global__ void slot_scale_kernel(uint32_t* __restrict__ meta, int max_count, int with_x) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float xmax = __uint_as_float(meta[2]);            // bits of max|X| (tc_absmax wrote them there)
+    if (with_x) xmax = fmaxf(xmax, 1.f);
+    meta[0] = __float_as_uint((float)max_count * xmax);
+    meta[1] = 0u;
+  }
+}
+__global__ void __launch_bounds__(256)
+kr_slot_sum_planes_kernel(const float* __restrict__ X, int64_t ldx, const int64_t* __restrict__ order,
+                          const int64_t* __restrict__ slot_start, const float* __restrict__ xn, int64_t P, int p,
+                          int nviews, int L, int with_x, __half* __restrict__ H, __half* __restrict__ Lo, int64_t ldp,
+                          const uint32_t* __restrict__ meta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int zcol0 = with_x ? nviews * p : 0;
+  const float sc = exp2f((float)(kF16Top - exp_of_bits(meta)));
+  for (int64_t s = warp; s < P * nviews; s += nwarps) {
+    const int64_t o = s / nviews;
+    const int v = (int)(s - o * nviews);
+    const int64_t b = slot_start[s], e = slot_start[s + 1];
+    const int64_t zoff = o * ldp + zcol0 + (int64_t)v * L;
+    for (int c = lane * 4; c < L; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t t = b; t < e; ++t) {
+        const float4 x = *reinterpret_cast<const float4*>(X + order[t] * ldx + c);
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+      }
+      uint2 h, l;
+      split4(acc, sc, h, l);
+      *reinterpret_cast<uint2*>(H + zoff + c) = h;
+      *reinterpret_cast<uint2*>(Lo + zoff + c) = l;
+    }
+    if (!with_x) continue;
+    const float cnt = (float)(e - b);
+    const int64_t xoff = o * ldp + (int64_t)v * p;
+    for (int c = lane * 4; c < p; c += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(xn + o * p + c);
+      uint2 h, l;
+      split4(make_float4(cnt * x.x, cnt * x.y, cnt * x.z, cnt * x.w), sc, h, l);
+      *reinterpret_cast<uint2*>(H + xoff + c) = h;
+      *reinterpret_cast<uint2*>(Lo + xoff + c) = l;
+    }
+  }
+}
+
 // ctas_per_sm > 0: one full wave of equal row blocks for a kernel that holds that many CTAs per SM; 0: 8 x SMs CTAs (the
 // upper bound the workspace is sized for).
 void split_grid(int64_t n, int cols, dim3& grid, int64_t& rows_per_block, int ctas_per_sm = 0) {
@@ -991,6 +1045,39 @@ int launch_pl_vb(const void* planesV, const float* Xb, int64_t ldxb, const float
   p.mode = 1; p.out = Vb; p.ldo = ldvb; p.alpha_host = 1.f;
   p.wave_ctr = reinterpret_cast<unsigned int*>(wsb + need - 256);
   return launch_pl_rows(pv, Q, &px, L, pb, n, Q, p, st);
+}
+
+// ---------------------------------------------------------------- structured route on planes
+// planes (P x nviews ((with_x ? p : 0) + L)) <- [cnt (x) xn | slot sums of X]; n = rows of X.
+int launch_kr_slot_sums_planes(const float* X, int64_t ldx, int64_t n, const int64_t* order, const int64_t* slot_start,
+                               const float* xn, int64_t P, int p, int nviews, int L, int with_x, int max_count,
+                               void* planes, cudaStream_t st) {
+  const int cols = nviews * ((with_x ? p : 0) + L);
+  PlanesView pv = planes_view(planes, P, cols);
+  GPP_TRY(tc_absmax(X, ldx, n, L, pv.meta + 2, st));
+  slot_scale_kernel<<<1, 32, 0, st>>>(pv.meta, max_count > 0 ? max_count : 1, with_x);
+  GPP_LAUNCH_CHECK();
+  const int64_t slots = P * nviews;
+  const int grid = (int)(ceil_div(slots, 8) < 8192 ? ceil_div(slots, 8) : 8192);
+  kr_slot_sum_planes_kernel<<<grid, 256, 0, st>>>(X, ldx, order, slot_start, xn, P, p, nviews, L, with_x, pv.hi, pv.lo,
+                                                  pv.ldp, pv.meta);
+  GPP_LAUNCH_CHECK();
+  return GPP_OK;
+}
+
+// out (n x ncols) = alpha A B with A (n x K) and B (K x ncols) as planes; ws: 256 bytes (wave counter)
+int launch_pl_am(const void* planesA, const void* planesB, int64_t n, int K, int ncols, float alpha, float* out,
+                 int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!ws || ws_bytes < 256) {
+    set_error("am (planes): workspace too small (%zu < 256 bytes)", ws_bytes);
+    return GPP_ERR_WORKSPACE;
+  }
+  const PlanesView pa = planes_view(const_cast<void*>(planesA), n, K);
+  const PlanesView pb = planes_view(const_cast<void*>(planesB), K, ncols);
+  PlRowsParams p{};
+  p.mode = 1; p.out = out; p.ldo = ldo; p.alpha_host = alpha;
+  p.wave_ctr = static_cast<unsigned int*>(ws);
+  return launch_pl_rows(pa, K, nullptr, 0, pb, n, ncols, p, st);
 }
 
 }  // namespace gpp

@@ -85,6 +85,12 @@ int launch_pl_vb(const void* planesV, const float* Xb, int64_t ldxb, const float
                  const double* scal, int64_t n, int Q, int L, int L_true, float* Vb, int64_t ldvb, void* ws,
                  size_t ws_bytes, cudaStream_t st);
 
+int launch_kr_slot_sums_planes(const float* X, int64_t ldx, int64_t n, const int64_t* order, const int64_t* slot_start,
+                               const float* xn, int64_t P, int p, int nviews, int L, int with_x, int max_count,
+                               void* planes, cudaStream_t st);
+int launch_pl_am(const void* planesA, const void* planesB, int64_t n, int K, int ncols, float alpha, float* out,
+                 int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
+
 bool tc_rows_supported(int64_t n, int K, int ncols);
 size_t tc_xb_workspace_bytes(int64_t n, int L);
 int launch_tc_xb(const float* V, int64_t ldv, const float* X, int64_t ldx, const float* W, int64_t ldw, int64_t n,

@@ -303,9 +303,7 @@ class GP(nn.Module):
     # ------------------------------------------------------------------ structured route (vmod.KhatriRao)
     def _kr_c(self, kr: KhatriRao, Xm, ldx, Lk) -> torch.Tensor:
         """C = V^T X (Q x Lk) through the slot sums, summed over the ranks."""
-        order, slot_start = kr.index()
-        XZ = ops.kr_slot_sums(Xm, ldx, order, slot_start, kr.xn, kr.nviews, Lk, False)
-        ST = ops.atb(kr.xn, kr.p, XZ, XZ.stride(0), kr.P, kr.p, XZ.shape[1])
+        ST = kr.st(Xm, ldx, Lk, False)
         self._all_reduce(ST)
         return ops.kr_assemble_gc(ST, kr.wn, kr.p, Lk, False)
 
@@ -323,10 +321,9 @@ class GP(nn.Module):
             ldx, Lx = 4, 4
         else:
             Lx = Lk
-        order, slot_start = kr.index()
+        kr.index()
         self._stage("pass1:start")
-        XZ = ops.kr_slot_sums(Xm, ldx, order, slot_start, kr.xn, kr.nviews, Lx, True)
-        ST = ops.atb(kr.xn, kr.p, XZ, XZ.stride(0), kr.P, kr.p, XZ.shape[1])
+        ST = kr.st(Xm, ldx, Lx, True)
         self._stage("pass1:end")
         self._all_reduce(ST)
         self._stage("allreduce:end")
@@ -341,7 +338,11 @@ class GP(nn.Module):
         W, scal = ops.solve_w(fac, C, C.stride(0), Lk, L, n_total)
         self._stage("solve:end")
         M = ops.kr_assemble_m(W, kr.wn, kr.p, Lk)
-        Y = ops.am(kr.xn, kr.p, M, M.stride(0), kr.P, kr.p, M.shape[1])
+        if ops.planes_supported(kr.P, kr.p, 0):
+            pM = ops.split_planes(M, M.stride(0), kr.p, M.shape[1])
+            Y = ops.am_planes(kr.xn_planes(), pM, kr.P, kr.p, M.shape[1])
+        else:
+            Y = ops.am(kr.xn, kr.p, M, M.stride(0), kr.P, kr.p, M.shape[1])
         Xb, nll = ops.kr_xb_nll(Xm, ldx, Y, kr.d, kr.w, kr.P, kr.nviews, Lk, scal)
         self._stage("pass2:end")
         return W, scal, Xb, nll

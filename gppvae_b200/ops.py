@@ -417,6 +417,34 @@ def kr_slot_sums(X: torch.Tensor, ldx: int, order: torch.Tensor, slot_start: tor
 
 
 @_on_device
+def kr_slot_sums_planes(X: torch.Tensor, ldx: int, order: torch.Tensor, slot_start: torch.Tensor, xn: torch.Tensor,
+                        nviews: int, L: int, with_x: bool, max_count: int) -> Planes:
+    """The matrix of `kr_slot_sums` written directly as operand planes (no fp32 copy, no scan of it)."""
+    lib = _lib.load()
+    P, p = xn.shape
+    cols = nviews * ((p if with_x else 0) + L)
+    with _guard(X):
+        buf = _workspace(lib.gpp_planes_bytes(P, cols), X.device)
+        check(lib.gpp_kr_slot_sums_planes(_p(X), ldx, X.shape[0], _p(order), _p(slot_start), _p(xn), P, p, nviews, L,
+                                          int(with_x), int(max_count), _p(buf), buf.numel(), _stream(X.device)),
+              "kr_slot_sums_planes")
+    return Planes(buf, P, cols, False)
+
+
+@_on_device
+def am_planes(pA: Planes, pM: Planes, n: int, k: int, m: int, alpha: float = 1.0) -> torch.Tensor:
+    """out (n x m) = alpha A M from operand planes."""
+    lib = _lib.load()
+    dev = pA.buf.device
+    with torch.cuda.device(dev):
+        out = torch.empty(n, m, device=dev, dtype=torch.float32)
+        ws = _workspace(256, dev)
+        check(lib.gpp_am_planes(pA.ptr, pM.ptr, n, k, m, float(alpha), _p(out), m, _p(ws), ws.numel(), _stream(dev)),
+              "am_planes")
+    return out
+
+
+@_on_device
 def kr_assemble_gc(ST: torch.Tensor, wn: torch.Tensor, p: int, L: int, with_g: bool) -> torch.Tensor:
     nv, q = wn.shape
     Q = p * q

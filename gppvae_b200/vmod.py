@@ -46,6 +46,8 @@ class KhatriRao:
         self.shape = torch.Size((self.n, p * self.q))
         self.device = xn.device
         self._index = None
+        self._max_count = None
+        self._xn_planes = None
 
     # -- index preparation (once per (d, w): the data set does not change between epochs) ------------------
     def index(self):
@@ -60,7 +62,32 @@ class KhatriRao:
             slot_start = torch.zeros(nslots + 1, dtype=torch.int64, device=self.device)
             torch.cumsum(counts, 0, out=slot_start[1:])
             self._index = (order.contiguous(), slot_start)
+            self._max_count = int(counts.max()) if counts.numel() else 0     # one host read per (d, w), with the index
         return self._index
+
+    def max_count(self) -> int:
+        """Rows in the fullest slot: bounds the slot sums when they are written as operand planes."""
+        if self._max_count is None:
+            self._index = None
+            self.index()
+        return self._max_count
+
+    def st(self, Xm: torch.Tensor, ldx: int, Lx: int, with_x: bool) -> torch.Tensor:
+        """ST = xn^T [cnt (x) xn | slot sums of X]  (p x nviews ((with_x ? p : 0) + Lx)).  From the tensor-core tile up
+        (P >= 512, p >= 128) the slot sums are written as operand planes and the P-long product runs on the planes
+        kernel; below that, an fp32 matrix and the kernel that splits its operands itself."""
+        order, slot_start = self.index()
+        if ops.planes_supported(self.P, self.p, 0):
+            pXZ = ops.kr_slot_sums_planes(Xm, ldx, order, slot_start, self.xn, self.nviews, Lx, with_x, self.max_count())
+            return ops.atb_planes(self.xn_planes(), pXZ, self.P, self.p, pXZ.cols)
+        XZ = ops.kr_slot_sums(Xm, ldx, order, slot_start, self.xn, self.nviews, Lx, with_x)
+        return ops.atb(self.xn, self.p, XZ, XZ.stride(0), self.P, self.p, XZ.shape[1])
+
+    def xn_planes(self):
+        """Operand planes of the normalised object table (the left operand of both P-long products), split once."""
+        if self._xn_planes is None:
+            self._xn_planes = ops.split_planes(self.xn, self.p, self.P, self.p, unit_bound=True)
+        return self._xn_planes
 
     # -- tensor-like surface the trainer touches -----------------------------------------------------------
     def detach(self) -> "KhatriRao":
@@ -77,10 +104,8 @@ class KhatriRao:
         Xm, ldx = ops.as_matrix(X, "X")
         if Xm.shape[0] != self.n:
             raise ValueError(f"X has {Xm.shape[0]} rows but V has {self.n}")
-        order, slot_start = self.index()
         Lk = Xm.shape[1]
-        XZ = ops.kr_slot_sums(Xm, ldx, order, slot_start, self.xn, self.nviews, Lk, False)
-        ST = ops.atb(self.xn, self.p, XZ, XZ.stride(0), self.P, self.p, XZ.shape[1])
+        ST = self.st(Xm, ldx, Lk, False)
         C = ops.kr_assemble_gc(ST, self.wn, self.p, Lk, False)
         q = self.q
         if self.p != self.p_true:
@@ -131,9 +156,9 @@ class Vmodel(nn.Module):
         key = (kr.d.data_ptr(), kr.d._version, kr.w.data_ptr(), kr.w._version, kr.n, kr.P, kr.nviews)
         cached = getattr(self, "_lazy_index", None)
         if cached is not None and cached[0] == key:
-            kr._index = cached[1]
+            kr._index, kr._max_count = cached[1], cached[3]
         else:
-            self._lazy_index = (key, kr.index(), (kr.d, kr.w))   # keeps d, w alive so the addresses stay theirs
+            self._lazy_index = (key, kr.index(), (kr.d, kr.w), kr.max_count())   # keeps d, w alive so the addresses stay theirs
         return kr
 
     def _init_params(self) -> None:

@@ -219,6 +219,18 @@ int gpp_am(const float* A, int64_t lda, const float* M, int64_t ldm, int64_t n, 
 int gpp_kr_slot_sums(const float* X, int64_t ldx, const int64_t* order, const int64_t* slot_start, const float* xn,
                      int64_t P, int32_t p, int32_t nviews, int32_t L, int32_t with_x, float* XZ, int64_t ldxz,
                      gpp_stream_t stream);
+/* The same two products on operand planes (shapes from the tensor-core tile up: P >= 512, p >= 128):
+ *   gpp_kr_slot_sums_planes  XZ written directly as planes (gpp_planes_bytes(P, nviews ((with_x ? p : 0) + L))): no fp32
+ *                            copy, and no scan of it -- the scale comes from the bound max_count * max(1, max|X|), with
+ *                            max_count = the largest number of rows in one slot (the caller knows it from the index)
+ *                            and max|X| from one read of X (n rows);  ST = xn^T XZ is then gpp_atb_planes.
+ *   gpp_am_planes            out = alpha A M from the planes of A (n x k) and M (k x m): Y = xn [M_0 | M_1 | ...];
+ *                            workspace: 256 bytes. */
+int gpp_kr_slot_sums_planes(const float* X, int64_t ldx, int64_t n, const int64_t* order, const int64_t* slot_start,
+                            const float* xn, int64_t P, int32_t p, int32_t nviews, int32_t L, int32_t with_x,
+                            int32_t max_count, void* planes, size_t planes_bytes, gpp_stream_t stream);
+int gpp_am_planes(const void* planesA, const void* planesB, int64_t n, int32_t k, int32_t m, float alpha, float* out,
+                  int64_t ldo, void* workspace, size_t workspace_bytes, gpp_stream_t stream);
 int gpp_kr_assemble_gc(const float* ST, int64_t ldst, const float* wn, int32_t p, int32_t q, int32_t nviews, int32_t L,
                        int32_t with_g, float* GC, int64_t ldgc, gpp_stream_t stream);
 int gpp_kr_assemble_m(const float* W, int64_t ldw, const float* wn, int32_t p, int32_t q, int32_t nviews, int32_t L,

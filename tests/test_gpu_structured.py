@@ -56,10 +56,13 @@ def test_structured_c1_against_oracle_and_dense(dev, kind, lvs):
     assert abs(nll.double().sum().item() - nll_d.double().sum().item()) / abs(nll_d.double().sum().item()) < NLL_TOL
 
 
-@pytest.mark.parametrize("n,P,nv,p,q,L", [(700, 37, 5, 8, 4, 12), (3000, 50, 7, 16, 7, 260), (513, 600, 3, 33, 4, 8)])
+@pytest.mark.parametrize("n,P,nv,p,q,L", [(700, 37, 5, 8, 4, 12), (3000, 50, 7, 16, 7, 260), (513, 600, 3, 33, 4, 8),
+                                          (6000, 640, 6, 128, 4, 72), (5000, 1500, 3, 130, 3, 64)])
 def test_structured_repeated_and_empty_slots(dev, n, P, nv, p, q, L):
     """Random (object, view) indices: slots that hold several rows and slots that hold none, widths that need padding
-    (p, L not multiples of 4), more views than view features -- against the fp64 oracle."""
+    (p, L not multiples of 4), more views than view features -- against the fp64 oracle.  The last two shapes (P >= 512,
+    p >= 128) take the operand-planes form of the P-long products (slot sums written as planes, scale from the slot-count
+    bound)."""
     import gppvae_b200
     from oracle import gp_oracle as O
     g = torch.Generator().manual_seed(n)
