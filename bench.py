@@ -464,33 +464,41 @@ def run_ours(args):
         check = run_check(args, gp, vm, pr, cfg, world, rank, dev)
 
     # ---- end to end: inputs start in pinned host memory, results end in pinned host memory, every step.
-    # The copy of Z rides a copy stream beside the work that does not need it (Khatri-Rao map, Gram tiles, Cholesky:
-    # GP.U_UBi_Shb, what train_gppvae.py:235 calls first anyway), and the results of step i leave on a third stream beside
-    # the compute of step i+1 (two sets of result buffers).  `sync_ms_per_step` is the same step with nothing pipelined
-    # across steps (submit, then wait for its results before the next submit).
+    # Pipelined leg: the inputs of step i+1 (d, w, Z) ride a copy stream beside the compute of step i (two sets of device
+    # buffers), the results of step i leave on a third stream beside the compute of step i+1 (two sets of host buffers) --
+    # every step still moves its own inputs and its own results inside the timed region (the last step's results are waited
+    # for before the clock stops), and the evaluation is the plain `vm(d, w)` + `gp.taylor_coeff(Z, [V])` of the
+    # device-resident leg.
+    # `sync_ms_per_step` is the same work with nothing pipelined across steps (submit, wait for the results, submit):
+    # there Z travels beside the work that does not need it (Khatri-Rao map, Gram tiles, Cholesky: GP.U_UBi_Shb, what
+    # train_gppvae.py:235 calls first anyway) and V^T Z follows as a launch of its own.
     _pin_to_local_numa(local)
     hd, hw, hZ = (t.cpu().pin_memory() for t in (pr.d, pr.w, pr.Z))
     h_out = [(torch.empty(n, 1).pin_memory(), torch.empty(n, L).pin_memory(), torch.empty(2).pin_memory())
              for _ in range(2)]
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    # device landing buffers of the inputs, double-buffered.  ALL of a step's inputs travel on the copy stream: the 16 MB
+    # of d, w issued on the compute stream queued behind the 1 GB of Z on the one host -> device copy engine and held the
+    # step's first kernel back by 8 ms (experiments/bench/e2e_trace.py).
+    Zd = [torch.empty_like(pr.Z) for _ in range(2)]
+    dd = [torch.empty_like(pr.d) for _ in range(2)]
+    wd = [torch.empty_like(pr.w) for _ in range(2)]
+    in_ready = [None, None]                                   # upload of buffer set k finished (recorded on s_in)
+    in_free = [None, None]                                    # last compute that read buffer set k finished (on main)
     out_done = [None, None]
     step_no = [0]
 
-    def e2e_submit():
-        i = step_no[0] & 1
-        step_no[0] += 1
-        main = torch.cuda.current_stream()
-        s_in.wait_stream(main)                      # Z's device buffer of two steps ago is free (allocator reuse)
+    def upload(k):
         with torch.cuda.stream(s_in):
-            Z = hZ.to(dev, non_blocking=True)
-            ev_in = torch.cuda.Event(); ev_in.record(s_in)
-        d = hd.to(dev, non_blocking=True); w = hw.to(dev, non_blocking=True)
-        with torch.no_grad():
-            V = vm(d, w)
-            gp.U_UBi_Shb([V], gp.get_vs())          # pass 1 (Gram) + Cholesky while Z is still on the wire
-            main.wait_event(ev_in)
-            Z.record_stream(main)
-            Xb, _, vbs, nll = gp.taylor_coeff(Z, [V], need_vb=False)   # factorisation reused: V^T Z, W, pass 2
+            if in_free[k] is not None:
+                s_in.wait_event(in_free[k])
+            dd[k].copy_(hd, non_blocking=True); wd[k].copy_(hw, non_blocking=True)
+            ev_dw = torch.cuda.Event(); ev_dw.record(s_in)
+            Zd[k].copy_(hZ, non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(s_in)
+        in_ready[k] = (ev_dw, ev)
+
+    def finish(i, main, Xb, vbs, nll):
         if out_done[i] is not None:
             out_done[i].synchronize()               # host buffers of slot i are ours again
         ev_c = torch.cuda.Event(); ev_c.record(main)
@@ -502,21 +510,59 @@ def run_ours(args):
             h_out[i][2].copy_(vbs, non_blocking=True)
             ev = torch.cuda.Event(); ev.record(s_out)
         out_done[i] = ev
+        return ev_c
+
+    def e2e_submit(prefetch_next=True):
+        i = step_no[0] & 1
+        step_no[0] += 1
+        main = torch.cuda.current_stream()
+        if in_ready[i] is None:                     # first step of a run: nothing was prefetched
+            upload(i)
+        ev_dw, ev_z = in_ready[i]
+        with torch.no_grad():
+            main.wait_event(ev_dw)
+            V = vm(dd[i], wd[i])
+            main.wait_event(ev_z)
+            Xb, _, vbs, nll = gp.taylor_coeff(Zd[i], [V], need_vb=False)
+        in_ready[i] = None
+        in_free[i] = finish(i, main, Xb, vbs, nll)
+        if prefetch_next:                           # step i+1's inputs start their way now, beside this step's compute
+            upload(i ^ 1)
         return i
+
+    def e2e_sync_step():
+        i = step_no[0] & 1
+        step_no[0] += 1
+        main = torch.cuda.current_stream()
+        upload(i)
+        ev_dw, ev_z = in_ready[i]
+        with torch.no_grad():
+            main.wait_event(ev_dw)
+            V = vm(dd[i], wd[i])
+            gp.U_UBi_Shb([V], gp.get_vs())          # pass 1 (Gram) + Cholesky while Z is still on the wire
+            main.wait_event(ev_z)
+            Xb, _, vbs, nll = gp.taylor_coeff(Zd[i], [V], need_vb=False)   # factorisation reused: V^T Z, W, pass 2
+        in_ready[i] = None
+        in_free[i] = finish(i, main, Xb, vbs, nll)
+        out_done[i].synchronize()
 
     def e2e_drain():
         for ev in out_done:
             if ev is not None:
                 ev.synchronize()
 
-    def timed_wall(fn, steps, warmup, drain):
+    def timed_wall(fn, steps, warmup, drain, last_arg=False):
+        """Wall time per step of `steps` calls of fn (+ the drain of whatever they left in flight).  With last_arg the
+        final call gets prefetch_next=False: no input is uploaded for a step that never runs."""
         for _ in range(warmup):
             fn()
+        if last_arg:
+            fn(False)
         drain()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
+        for k in range(steps):
+            fn(k + 1 < steps) if last_arg else fn()
         drain()
         torch.cuda.synchronize()
         ms = torch.tensor([1e3 * (time.perf_counter() - t0) / steps], device=dev, dtype=torch.float64)
@@ -524,11 +570,7 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def e2e_sync_step():
-        i = e2e_submit()
-        out_done[i].synchronize()
-
-    ms_e2e = timed_wall(e2e_submit, args.steps, 2, e2e_drain)
+    ms_e2e = timed_wall(e2e_submit, args.steps, 2, e2e_drain, last_arg=True)
     ms_e2e_sync = timed_wall(e2e_sync_step, max(2, min(args.steps, 5)), 1, e2e_drain)
     last = (step_no[0] - 1) & 1
     h_nll, h_Xb, h_vbs = h_out[last]
@@ -615,10 +657,12 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": launches, "engine": _lib.gemm_engine(),
         "e2e": {"value": N / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "sync_ms_per_step": ms_e2e_sync, "pipelined_steps_in_flight": 2,
-                "api": "Vmodel.forward + GP.U_UBi_Shb + GP.taylor_coeff(need_vb=False) from pinned host tensors (Z on a "
-                       "copy stream beside the Gram tiles and the Cholesky); nll, Xb, vbs copied back to pinned host "
-                       "memory on a third stream beside the next step's compute; sync_ms_per_step waits for each step's "
-                       "results before submitting the next",
+                "api": "Vmodel.forward + GP.taylor_coeff(need_vb=False) from pinned host tensors, every step: d, w, Z host -> "
+                       "device (step i+1's Z on a copy stream beside the compute of step i, two device buffers), nll, Xb, vbs "
+                       "device -> pinned host on a third stream beside the next step's compute; the last step's results are "
+                       "waited for inside the timed region.  sync_ms_per_step: nothing pipelined across steps (Z beside "
+                       "Vmodel.forward + GP.U_UBi_Shb, then GP.taylor_coeff on the cached factorisation; each step waits "
+                       "for its own results before the next one is submitted)",
                 "c_entry_ms_per_step": ms_c, "c_entry_sync_ms_per_step": ms_c_sync,
                 "c_entry": "gpp_gp_term_host_submit / _wait (same pipeline inside libgppvae_b200.so)"},
         "roofline": {"bound": "tensor", "kernel": "pass 1: V^T[V|Z] (pl_pass1_kernel + tc_reduce_kernel + tc_mirror_kernel; "

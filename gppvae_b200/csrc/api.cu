@@ -475,17 +475,20 @@ extern "C" int gpp_gp_term_host_submit(gpp_host_ctx* ctx, const float* x0_host, 
   double* scal = reinterpret_cast<double*>(a + o_scal);
   cudaStream_t st = ctx->compute;
 
-  // copy-in stream: X -> slot s, once the compute that last read this slot's X is done
-  if (ctx->used[s]) GPP_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->comp_done[s], 0));
-  GPP_CUDA(cudaMemcpyAsync(F(o_X[s]), X_host, (size_t)n * L * 4, cudaMemcpyHostToDevice, ctx->copy_in));
-  GPP_CUDA(cudaEventRecord(ctx->in_done[s], ctx->copy_in));
-
-  // compute stream: everything that does not need X
+  // compute stream: everything that does not need X.  The small uploads are ISSUED before the large one: there is one
+  // host -> device copy engine, it serves copies in issue order, and the 16 MB of d, w queued behind the 1 GB of X held
+  // the first kernel of the step back by 8 ms (experiments/bench/e2e_trace.py).
   GPP_CUDA(cudaMemcpyAsync(F(o_x0), x0_host, (size_t)P * p * 4, cudaMemcpyHostToDevice, st));
   GPP_CUDA(cudaMemcpyAsync(F(o_v0), v0_host, (size_t)nviews * q * 4, cudaMemcpyHostToDevice, st));
   GPP_CUDA(cudaMemcpyAsync(d_dev, d_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   GPP_CUDA(cudaMemcpyAsync(w_dev, w_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   GPP_CUDA(cudaMemcpyAsync(F(o_lvs), lvs_host, 8, cudaMemcpyHostToDevice, st));
+
+  // copy-in stream: X -> slot s, once the compute that last read this slot's X is done
+  if (ctx->used[s]) GPP_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->comp_done[s], 0));
+  GPP_CUDA(cudaMemcpyAsync(F(o_X[s]), X_host, (size_t)n * L * 4, cudaMemcpyHostToDevice, ctx->copy_in));
+  GPP_CUDA(cudaEventRecord(ctx->in_done[s], ctx->copy_in));
+
   GPP_TRY(gpp_normalize_rows_fwd(F(o_x0), P, p, F(o_xn), st));
   GPP_TRY(gpp_normalize_rows_fwd(F(o_v0), nviews, q, F(o_wn), st));
   softmax2_kernel<<<1, 32, 0, st>>>(F(o_lvs), F(o_vs));
