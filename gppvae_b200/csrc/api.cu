@@ -348,14 +348,19 @@ __global__ void softmax2_kernel(const float* __restrict__ lvs, float* __restrict
 }  // namespace gpp
 
 // The host-buffer entry overlaps the PCIe copies with the compute they do not feed:
-//   copy-in stream : X (the N x L latent matrix, the only large input) -> device
-//   compute stream : tables, indices, Khatri-Rao map + planes, the Gram tiles of pass 1 and the Cholesky -- none of which
-//                    needs X -- then (after the copy-in event) split X, V^T X, W, pass 2
+//   copy-in stream : ALL inputs -> device, the small ones (tables, indices, lvs) first, then X (the N x L latent matrix),
+//                    every one double-buffered (slot s), so that a submission's inputs can travel while the previous
+//                    submission computes.  One stream because the order matters and nothing else guarantees it: there is
+//                    one host -> device copy engine, and the 16 MB of d, w queued behind the 1 GB of X hold the first
+//                    kernel back by the whole transfer (experiments/bench/e2e_trace.py, c_entry_trace.py)
+//   compute stream : (after the small-inputs event) tables, Khatri-Rao map + planes, the Gram tiles of pass 1 and the
+//                    Cholesky -- none of which needs X -- then (after the copy-in event) split X, V^T X, W, pass 2
 //   copy-out stream: nll, Xb, vbs -> host, behind the compute of the NEXT submission (two host-facing buffer sets)
 // gpp_gp_term_host_submit / _wait expose that pipeline; gpp_gp_term_host = submit + wait.
 struct gpp_host_ctx {
   cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+  cudaEvent_t small_done[2] = {nullptr, nullptr};
   bool out_pending[2] = {false, false}, used[2] = {false, false};
   void* arena = nullptr;
   size_t arena_bytes = 0;
@@ -372,6 +377,7 @@ extern "C" int gpp_host_ctx_create(gpp_host_ctx** ctx) {
     e = cudaEventCreateWithFlags(&c->in_done[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->comp_done[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->out_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->small_done[i], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
     gpp_host_ctx_destroy(c);
@@ -391,6 +397,7 @@ extern "C" int gpp_host_ctx_destroy(gpp_host_ctx* ctx) {
     if (ctx->in_done[i]) cudaEventDestroy(ctx->in_done[i]);
     if (ctx->comp_done[i]) cudaEventDestroy(ctx->comp_done[i]);
     if (ctx->out_done[i]) cudaEventDestroy(ctx->out_done[i]);
+    if (ctx->small_done[i]) cudaEventDestroy(ctx->small_done[i]);
   }
   if (ctx->compute) cudaStreamDestroy(ctx->compute);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -431,12 +438,15 @@ extern "C" int gpp_gp_term_host_submit(gpp_host_ctx* ctx, const float* x0_host, 
     off += align_up(bytes, 256);
     return o;
   };
-  const size_t o_x0 = take((size_t)P * p * 4), o_xn = take((size_t)P * p * 4);
-  const size_t o_v0 = take((size_t)nviews * q * 4), o_wn = take((size_t)nviews * q * 4);
-  const size_t o_d = take((size_t)n * 8), o_w = take((size_t)n * 8);
-  const size_t o_lvs = take(16), o_vs = take(16), o_scal = take(GPP_NSCAL * 8), o_vbs = take(16);
-  size_t o_X[2], o_Xb[2], o_nll[2];
+  const size_t o_xn = take((size_t)P * p * 4), o_wn = take((size_t)nviews * q * 4);
+  const size_t o_vs = take(16), o_scal = take(GPP_NSCAL * 8), o_vbs = take(16);
+  size_t o_x0s[2], o_v0s[2], o_ds[2], o_wsl[2], o_lvss[2], o_X[2], o_Xb[2], o_nll[2];
   for (int i = 0; i < 2; ++i) {
+    o_x0s[i] = take((size_t)P * p * 4);
+    o_v0s[i] = take((size_t)nviews * q * 4);
+    o_ds[i] = take((size_t)n * 8);
+    o_wsl[i] = take((size_t)n * 8);
+    o_lvss[i] = take(16);
     o_X[i] = take((size_t)n * L * 4);
     o_Xb[i] = take((size_t)n * L * 4);
     o_nll[i] = take((size_t)n * 4);
@@ -470,25 +480,26 @@ extern "C" int gpp_gp_term_host_submit(gpp_host_ctx* ctx, const float* x0_host, 
   }
   char* a = static_cast<char*>(ctx->arena);
   auto F = [&](size_t o) { return reinterpret_cast<float*>(a + o); };
-  int64_t* d_dev = reinterpret_cast<int64_t*>(a + o_d);
-  int64_t* w_dev = reinterpret_cast<int64_t*>(a + o_w);
+  const size_t o_x0 = o_x0s[s], o_v0 = o_v0s[s], o_lvs = o_lvss[s];
+  int64_t* d_dev = reinterpret_cast<int64_t*>(a + o_ds[s]);
+  int64_t* w_dev = reinterpret_cast<int64_t*>(a + o_wsl[s]);
   double* scal = reinterpret_cast<double*>(a + o_scal);
   cudaStream_t st = ctx->compute;
 
-  // compute stream: everything that does not need X.  The small uploads are ISSUED before the large one: there is one
-  // host -> device copy engine, it serves copies in issue order, and the 16 MB of d, w queued behind the 1 GB of X held
-  // the first kernel of the step back by 8 ms (experiments/bench/e2e_trace.py).
-  GPP_CUDA(cudaMemcpyAsync(F(o_x0), x0_host, (size_t)P * p * 4, cudaMemcpyHostToDevice, st));
-  GPP_CUDA(cudaMemcpyAsync(F(o_v0), v0_host, (size_t)nviews * q * 4, cudaMemcpyHostToDevice, st));
-  GPP_CUDA(cudaMemcpyAsync(d_dev, d_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  GPP_CUDA(cudaMemcpyAsync(w_dev, w_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  GPP_CUDA(cudaMemcpyAsync(F(o_lvs), lvs_host, 8, cudaMemcpyHostToDevice, st));
+  // copy-in stream: the inputs of slot s, once the compute that last read this slot is done; small ones first
+  cudaStream_t ci = ctx->copy_in;
+  if (ctx->used[s]) GPP_CUDA(cudaStreamWaitEvent(ci, ctx->comp_done[s], 0));
+  GPP_CUDA(cudaMemcpyAsync(F(o_x0), x0_host, (size_t)P * p * 4, cudaMemcpyHostToDevice, ci));
+  GPP_CUDA(cudaMemcpyAsync(F(o_v0), v0_host, (size_t)nviews * q * 4, cudaMemcpyHostToDevice, ci));
+  GPP_CUDA(cudaMemcpyAsync(d_dev, d_host, (size_t)n * 8, cudaMemcpyHostToDevice, ci));
+  GPP_CUDA(cudaMemcpyAsync(w_dev, w_host, (size_t)n * 8, cudaMemcpyHostToDevice, ci));
+  GPP_CUDA(cudaMemcpyAsync(F(o_lvs), lvs_host, 8, cudaMemcpyHostToDevice, ci));
+  GPP_CUDA(cudaEventRecord(ctx->small_done[s], ci));
+  GPP_CUDA(cudaMemcpyAsync(F(o_X[s]), X_host, (size_t)n * L * 4, cudaMemcpyHostToDevice, ci));
+  GPP_CUDA(cudaEventRecord(ctx->in_done[s], ci));
 
-  // copy-in stream: X -> slot s, once the compute that last read this slot's X is done
-  if (ctx->used[s]) GPP_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->comp_done[s], 0));
-  GPP_CUDA(cudaMemcpyAsync(F(o_X[s]), X_host, (size_t)n * L * 4, cudaMemcpyHostToDevice, ctx->copy_in));
-  GPP_CUDA(cudaEventRecord(ctx->in_done[s], ctx->copy_in));
-
+  // compute stream: everything that does not need X
+  GPP_CUDA(cudaStreamWaitEvent(st, ctx->small_done[s], 0));
   GPP_TRY(gpp_normalize_rows_fwd(F(o_x0), P, p, F(o_xn), st));
   GPP_TRY(gpp_normalize_rows_fwd(F(o_v0), nviews, q, F(o_wn), st));
   softmax2_kernel<<<1, 32, 0, st>>>(F(o_lvs), F(o_vs));
