@@ -254,8 +254,10 @@ int gpp_taylor_expansion_bwd(const float* gout, const float* Xb, int64_t ldxb, c
 
 /* One evaluation of the GP term from HOST buffers: copies x0, v0, d, w, X, lvs to the device, builds V
  * (vmod.py:22-35), runs pass 1 / factor / pass 2 (gp.py:55-60,84-87) and copies nll (n), Xb (n x L) and vbs[2] back.
- * The copy of X runs on its own stream beside the work that does not need it (the Khatri-Rao map, the Gram tiles of
- * pass 1, the Cholesky), and the results leave on a third stream beside the compute of the NEXT submission:
+ * All inputs travel on one copy stream, the small ones first, into one of two sets of device buffers: X is on the wire
+ * beside the work that does not need it (the Khatri-Rao map, the Gram tiles of pass 1, the Cholesky), the inputs of a
+ * second submission beside the compute of the first, and the results leave on a third stream beside the compute of the
+ * NEXT submission:
  *   gpp_gp_term_host_submit  enqueues one evaluation and returns a ticket (0 or 1: two sets of host-facing device
  *                            buffers); at most two submissions are in flight -- a third first waits for the oldest;
  *   gpp_gp_term_host_wait    blocks until the results of that ticket are in the host buffers;
