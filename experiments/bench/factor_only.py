@@ -16,6 +16,7 @@ C = torch.randn(Q, 256, device=dev)
 vs = torch.tensor([0.5, 0.5], device=dev)
 for _ in range(2):
     f = ops.factor(G, Q, Q, vs, False)
+    ops.solve_w(f, C, 256, 256, 256, 100000)      # (warm-up of solve_w too: its first calls allocate)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 for _ in range(reps):
